@@ -1,0 +1,103 @@
+// Shared host-side plumbing: error propagation (no exceptions leave the library), RAII device buffers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/sivo_b200.h"
+
+namespace sivo {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+[[noreturn]] inline void fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw Error(code, buf);
+}
+
+void set_last_error(const std::string& m);
+
+#define SIVO_CUDA(expr)                                                                          \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      ::sivo::fail(SIVO_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+// Wraps a C-ABI body: translates exceptions into codes + thread-local message.
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return SIVO_OK;
+  } catch (const Error& e) {
+    set_last_error(e.what());
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    set_last_error("out of host memory");
+    return SIVO_ENOMEM;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return SIVO_EINVAL;
+  }
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t n) { alloc(n); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    SIVO_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  PinnedBuf() = default;
+  PinnedBuf(const PinnedBuf&) = delete;
+  PinnedBuf& operator=(const PinnedBuf&) = delete;
+  ~PinnedBuf() { if (p) cudaFreeHost(p); }
+  void ensure(size_t n) {
+    if (n <= bytes) return;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    SIVO_CUDA(cudaMallocHost(&p, n));
+    bytes = n;
+  }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace sivo

@@ -1,0 +1,98 @@
+// ORB extractor: host twin of `SIVO::ORBextractor` (src/orbslam/ORBextractor.cc) driving the kernels in
+// orb_kernels.cu.  One instance = one CUDA stream + its own workspace, so two instances can run
+// concurrently from two threads as Frame.cc:126-129 does.
+#pragma once
+#include <vector>
+
+#include "common.h"
+
+namespace sivo {
+
+constexpr int kOrbMaxLevels = 16;
+constexpr int kEdge = 19;        // EDGE_THRESHOLD (ORBextractor.cc:72)
+constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE
+constexpr int kCellCap = 1024;   // per-cell candidate slots (3x3 NMS keeps <= 1/4 of a <= 62x62 interior)
+
+struct OrbLevel {
+  int w, h;            // level image size
+  int pitch;           // bytes per row of the bordered buffer ((w + 38) rounded up to 16)
+  size_t img_off;      // offset of the bordered buffer in the pyramid arena
+  size_t flat_off;     // offset of the w*h planes (score map, blurred image) in their arenas
+  int cell_begin, cell_end;
+};
+
+struct OrbCell {
+  int level;
+  short x0, y0, x1, y1;  // FAST sub-image rectangle in level coordinates (ORBextractor.cc:776-798)
+};
+
+struct OrbLevelTable {
+  int nlevels;
+  OrbLevel lv[kOrbMaxLevels];
+};
+
+struct OrbSelected {  // one retained keypoint, level coordinates
+  short x, y;
+  short level;
+  short pad;
+};
+
+// ---- kernels (orb_kernels.cu)
+void orb_launch_pyramid(const uint8_t* gray, int rows, int cols, size_t gray_pitch, uint8_t* pyr, const OrbLevelTable& t,
+                        cudaStream_t s);
+void orb_launch_score(const uint8_t* pyr, uint8_t* score, const OrbLevelTable& t, cudaStream_t s);
+void orb_launch_cells(const uint8_t* score, const OrbLevelTable& t, const OrbCell* cells, int ncells, int ini_th, int min_th,
+                      int* cell_count, uint32_t* cell_items, cudaStream_t s);
+void orb_launch_compact(const OrbLevelTable& t, const OrbCell* cells, int ncells, const int* cell_count,
+                        const uint32_t* cell_items, int* cell_offset, int* level_offsets, uint32_t* cand, int cand_cap,
+                        cudaStream_t s);
+void orb_launch_blur(const uint8_t* pyr, uint8_t* blur, const OrbLevelTable& t, cudaStream_t s);
+void orb_launch_describe(const uint8_t* pyr, const uint8_t* blur, const OrbLevelTable& t, const OrbSelected* sel, int n,
+                         const int* umax, float* angles, uint8_t* desc, cudaStream_t s);
+void orb_upload_pattern();  // copies the rBRIEF pair table into constant memory (once per device)
+
+// ---- host (orb_host.cu)
+struct OrbTables {
+  std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+  std::vector<int> per_level;
+  int umax[kHalfPatch + 1];
+};
+OrbTables orb_make_tables(int nfeatures, float scale_factor, int nlevels);
+
+// DistributeOctTree (ORBextractor.cc:544-750) with the documented tie rule; returns kept indices in
+// the reference's output order.
+std::vector<int> orb_distribute(const float* xs, const float* ys, const float* resp, int n, int min_x, int max_x, int min_y,
+                                int max_y, int n_target);
+
+class Orb {
+ public:
+  Orb(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int device);
+  ~Orb();
+  void run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypoint* kps, int cap, int* n, uint8_t* desc,
+           uint8_t* const* pyr_out, const size_t* pyr_strides);
+  void level_size(int rows, int cols, int level, int* w, int* h) const;
+  const OrbTables& tables() const { return tab_; }
+  int nlevels() const { return nlevels_; }
+  void candidates(int level, int* xs, int* ys, int* resp, int cap, int* n) const;
+  float device_ms = 0, tree_ms = 0;
+  int launches = 0;
+
+ private:
+  void ensure(int rows, int cols);
+  int nfeatures_, nlevels_, ini_th_, min_th_, device_;
+  float scale_factor_;
+  OrbTables tab_;
+  int rows_ = 0, cols_ = 0;
+  OrbLevelTable lt_{};
+  std::vector<OrbCell> cells_;
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+  DevBuf d_gray_, d_pyr_, d_score_, d_blur_, d_cells_, d_cell_count_, d_cell_items_, d_cell_offset_, d_level_off_, d_cand_,
+      d_sel_, d_umax_, d_angles_, d_desc_;
+  PinnedBuf h_gray_, h_cand_, h_level_off_, h_sel_, h_angles_, h_desc_, h_pyr_;
+  size_t pyr_bytes_ = 0, flat_bytes_ = 0;
+  int cand_cap_ = 0, sel_cap_ = 0;
+  std::vector<std::vector<int>> last_cand_;  // per level: x, y, resp triples (test hook)
+};
+
+}  // namespace sivo

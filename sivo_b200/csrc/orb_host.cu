@@ -1,0 +1,437 @@
+// Host side of the ORB operator: constructor tables, the per-level cell grid, the quad-tree keypoint
+// distribution (order dependent and tiny -- stays on the host), and the two-phase device schedule
+//   [pyramid, score, cells, compact, blur] -> candidates D2H -> quad tree -> selection H2D -> [angle+rBRIEF] -> D2H.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "orb.h"
+
+namespace sivo {
+
+// ---------------------------------------------------------------- ORBextractor::ORBextractor (:412-475)
+OrbTables orb_make_tables(int nfeatures, float scale_factor, int nlevels) {
+  OrbTables t;
+  const double sf = static_cast<double>(scale_factor);  // the member is a double initialised from the float argument
+  t.scale.assign(nlevels, 1.f);
+  t.sigma2.assign(nlevels, 1.f);
+  for (int i = 1; i < nlevels; ++i) {
+    t.scale[i] = static_cast<float>(t.scale[i - 1] * sf);
+    t.sigma2[i] = t.scale[i] * t.scale[i];
+  }
+  t.inv_scale.resize(nlevels);
+  t.inv_sigma2.resize(nlevels);
+  for (int i = 0; i < nlevels; ++i) {
+    t.inv_scale[i] = 1.0f / t.scale[i];
+    t.inv_sigma2[i] = 1.0f / t.sigma2[i];
+  }
+  t.per_level.assign(nlevels, 0);
+  const float factor = static_cast<float>(1.0f / sf);
+  float desired = nfeatures * (1 - factor) / (1 - static_cast<float>(std::pow(static_cast<double>(factor), static_cast<double>(nlevels))));
+  int sum = 0;
+  for (int l = 0; l < nlevels - 1; ++l) {
+    t.per_level[l] = static_cast<int>(std::nearbyint(desired));
+    sum += t.per_level[l];
+    desired *= factor;
+  }
+  t.per_level[nlevels - 1] = std::max(nfeatures - sum, 0);
+  // end of each row of the radius-15 disc
+  const float hs = kHalfPatch * std::sqrt(2.f) / 2;
+  const int vmax = static_cast<int>(std::floor(hs + 1));
+  const int vmin = static_cast<int>(std::ceil(hs));
+  const double hp2 = kHalfPatch * kHalfPatch;
+  for (int v = 0; v <= kHalfPatch; ++v) t.umax[v] = 0;
+  for (int v = 0; v <= vmax; ++v) t.umax[v] = static_cast<int>(std::nearbyint(std::sqrt(hp2 - v * v)));
+  for (int v = kHalfPatch, v0 = 0; v >= vmin; --v) {
+    while (t.umax[v0] == t.umax[v0 + 1]) ++v0;
+    t.umax[v] = v0;
+    ++v0;
+  }
+  return t;
+}
+
+// ---------------------------------------------------------------- DistributeOctTree (:544-750)
+namespace {
+struct QNode {
+  int ulx, uly, urx, bry;
+  std::vector<int> keys;
+  bool no_more = false;
+  int prev = -1, next = -1;  // intrusive list links (arena indices)
+  int seq = 0;               // creation order among splittable nodes: the documented tie-break
+};
+
+struct QList {
+  std::vector<QNode> arena;
+  int head = -1, tail = -1, size = 0;
+  int make() { arena.emplace_back(); return static_cast<int>(arena.size()) - 1; }
+  void push_front(int i) {
+    arena[i].prev = -1;
+    arena[i].next = head;
+    if (head >= 0) arena[head].prev = i; else tail = i;
+    head = i;
+    ++size;
+  }
+  void push_back(int i) {
+    arena[i].next = -1;
+    arena[i].prev = tail;
+    if (tail >= 0) arena[tail].next = i; else head = i;
+    tail = i;
+    ++size;
+  }
+  int erase(int i) {  // returns the successor
+    int p = arena[i].prev, n = arena[i].next;
+    if (p >= 0) arena[p].next = n; else head = n;
+    if (n >= 0) arena[n].prev = p; else tail = p;
+    --size;
+    return n;
+  }
+};
+}  // namespace
+
+std::vector<int> orb_distribute(const float* xs, const float* ys, const float* resp, int n, int min_x, int max_x, int min_y,
+                                int max_y, int n_target) {
+  std::vector<int> result;
+  if (n <= 0) return result;
+  QList L;
+  L.arena.reserve(static_cast<size_t>(n) * 4 + 64);
+  int n_ini = static_cast<int>(std::round(static_cast<float>(max_x - min_x) / (max_y - min_y)));
+  if (n_ini < 1) n_ini = 1;  // the reference divides by zero here for tall images; not reachable on this path
+  const float hx = static_cast<float>(max_x - min_x) / n_ini;
+  std::vector<int> ini(n_ini);
+  for (int i = 0; i < n_ini; ++i) {
+    int id = L.make();
+    QNode& nd = L.arena[id];
+    nd.ulx = static_cast<int>(hx * static_cast<float>(i));
+    nd.urx = static_cast<int>(hx * static_cast<float>(i + 1));
+    nd.uly = 0;
+    nd.bry = max_y - min_y;
+    L.push_back(id);
+    ini[i] = id;
+  }
+  for (int k = 0; k < n; ++k) {
+    int cell = static_cast<int>(xs[k] / hx);
+    if (cell >= n_ini) cell = n_ini - 1;
+    L.arena[ini[cell]].keys.push_back(k);
+  }
+  for (int i = L.head; i >= 0;) {
+    QNode& nd = L.arena[i];
+    if (nd.keys.size() == 1) { nd.no_more = true; i = nd.next; }
+    else if (nd.keys.empty()) i = L.erase(i);
+    else i = nd.next;
+  }
+  int seq = 0;
+  std::vector<int> pending;  // splittable children created in the current round
+  auto split = [&](int id, int& n_expand) {
+    // ExtractorNode::DivideNode (:488-542)
+    const int ulx = L.arena[id].ulx, uly = L.arena[id].uly, urx = L.arena[id].urx, bry = L.arena[id].bry;
+    const int half_x = static_cast<int>(std::ceil(static_cast<float>(urx - ulx) / 2));
+    const int half_y = static_cast<int>(std::ceil(static_cast<float>(bry - uly) / 2));
+    const int mx = ulx + half_x, my = uly + half_y;
+    int c[4];
+    for (int q = 0; q < 4; ++q) c[q] = L.make();
+    auto set = [&](int q, int a, int b, int cc, int d) {
+      QNode& nd = L.arena[c[q]];
+      nd.ulx = a; nd.uly = b; nd.urx = cc; nd.bry = d;
+    };
+    set(0, ulx, uly, mx, my);
+    set(1, mx, uly, urx, my);
+    set(2, ulx, my, mx, bry);
+    set(3, mx, my, urx, bry);
+    const std::vector<int> keys = L.arena[id].keys;  // copy: the arena may reallocate below
+    for (int k : keys) {
+      int q = xs[k] < mx ? (ys[k] < my ? 0 : 2) : (ys[k] < my ? 1 : 3);
+      L.arena[c[q]].keys.push_back(k);
+    }
+    for (int q = 0; q < 4; ++q) {
+      QNode& nd = L.arena[c[q]];
+      if (nd.keys.size() == 1) nd.no_more = true;
+      if (!nd.keys.empty()) {
+        L.push_front(c[q]);
+        if (nd.keys.size() > 1) {
+          ++n_expand;
+          nd.seq = ++seq;
+          pending.push_back(c[q]);
+        }
+      }
+    }
+  };
+  bool finish = false;
+  while (!finish) {
+    const int prev_size = L.size;
+    int n_expand = 0;
+    pending.clear();
+    for (int i = L.head; i >= 0;) {
+      if (L.arena[i].no_more) { i = L.arena[i].next; continue; }
+      split(i, n_expand);
+      i = L.erase(i);
+    }
+    if (L.size >= n_target || L.size == prev_size) {
+      finish = true;
+    } else if (L.size + n_expand * 3 > n_target) {
+      while (!finish) {
+        const int prev = L.size;
+        std::vector<int> round = pending;
+        pending.clear();
+        // std::sort on (size, ExtractorNode*) in the reference (:671-676); ties by creation order here
+        std::sort(round.begin(), round.end(), [&](int a, int b) {
+          size_t sa = L.arena[a].keys.size(), sb = L.arena[b].keys.size();
+          return sa != sb ? sa < sb : L.arena[a].seq < L.arena[b].seq;
+        });
+        for (int j = static_cast<int>(round.size()) - 1; j >= 0; --j) {
+          int dummy = 0;
+          split(round[j], dummy);
+          L.erase(round[j]);
+          if (L.size >= n_target) break;
+        }
+        if (L.size >= n_target || L.size == prev) finish = true;
+      }
+    }
+  }
+  result.reserve(L.size);
+  for (int i = L.head; i >= 0; i = L.arena[i].next) {
+    const std::vector<int>& keys = L.arena[i].keys;
+    int best = keys[0];
+    for (size_t k = 1; k < keys.size(); ++k)
+      if (resp[keys[k]] > resp[best]) best = keys[k];
+    result.push_back(best);
+  }
+  return result;
+}
+
+// ---------------------------------------------------------------- Orb
+namespace {
+std::once_flag g_pattern_once[64];
+int cv_round_f(float v) { return static_cast<int>(std::nearbyint(v)); }
+}  // namespace
+
+Orb::Orb(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int device)
+    : nfeatures_(nfeatures), nlevels_(nlevels), ini_th_(ini_th), min_th_(min_th), device_(device), scale_factor_(scale_factor) {
+  if (nfeatures <= 0 || nlevels <= 0 || nlevels > kOrbMaxLevels || !(scale_factor > 1.f) || ini_th <= 0 || min_th <= 0 ||
+      ini_th > 255 || min_th > 255)
+    fail(SIVO_EINVAL, "ORBextractor: bad parameters (nfeatures %d, scale %.3f, levels %d, th %d/%d)", nfeatures, scale_factor,
+         nlevels, ini_th, min_th);
+  tab_ = orb_make_tables(nfeatures, scale_factor, nlevels);
+  SIVO_CUDA(cudaSetDevice(device_));
+  std::call_once(g_pattern_once[device_ & 63], [] { orb_upload_pattern(); });
+  SIVO_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  for (auto& e : ev_) SIVO_CUDA(cudaEventCreate(&e));
+  d_umax_.alloc(sizeof(tab_.umax));
+  SIVO_CUDA(cudaMemcpy(d_umax_.p, tab_.umax, sizeof(tab_.umax), cudaMemcpyHostToDevice));
+  sel_cap_ = nfeatures + 4 * nlevels + 64;
+  d_sel_.alloc(sel_cap_ * sizeof(OrbSelected));
+  d_angles_.alloc(sel_cap_ * sizeof(float));
+  d_desc_.alloc(static_cast<size_t>(sel_cap_) * 32);
+  h_sel_.ensure(sel_cap_ * sizeof(OrbSelected));
+  h_angles_.ensure(sel_cap_ * sizeof(float));
+  h_desc_.ensure(static_cast<size_t>(sel_cap_) * 32);
+  d_level_off_.alloc((kOrbMaxLevels + 1) * sizeof(int));
+  h_level_off_.ensure((kOrbMaxLevels + 1) * sizeof(int));
+}
+
+Orb::~Orb() {
+  cudaSetDevice(device_);
+  for (auto& e : ev_) if (e) cudaEventDestroy(e);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+void Orb::level_size(int rows, int cols, int level, int* w, int* h) const {
+  if (level < 0 || level >= nlevels_) fail(SIVO_EINVAL, "level %d out of range", level);
+  // ComputePyramid (:1086-1089)
+  float s = tab_.inv_scale[level];
+  if (w) *w = cv_round_f(static_cast<float>(cols) * s);
+  if (h) *h = cv_round_f(static_cast<float>(rows) * s);
+}
+
+void Orb::ensure(int rows, int cols) {
+  if (rows == rows_ && cols == cols_) return;
+  lt_.nlevels = nlevels_;
+  cells_.clear();
+  size_t img_off = 0, flat_off = 0;
+  for (int l = 0; l < nlevels_; ++l) {
+    OrbLevel& lv = lt_.lv[l];
+    level_size(rows, cols, l, &lv.w, &lv.h);
+    if (lv.w < 2 * kEdge + 7 || lv.h < 2 * kEdge + 7)
+      fail(SIVO_EINVAL, "image %dx%d is too small for %d pyramid levels", cols, rows, nlevels_);
+    lv.pitch = (lv.w + 2 * kEdge + 15) / 16 * 16;
+    lv.img_off = img_off;
+    lv.flat_off = flat_off;
+    img_off += static_cast<size_t>(lv.pitch) * (lv.h + 2 * kEdge);
+    img_off = (img_off + 255) / 256 * 256;
+    flat_off += static_cast<size_t>(lv.w) * lv.h;
+    flat_off = (flat_off + 255) / 256 * 256;
+    // cell grid of ComputeKeyPointsOctTree (:759-791)
+    const int min_bx = kEdge - 3, min_by = kEdge - 3, max_bx = lv.w - kEdge + 3, max_by = lv.h - kEdge + 3;
+    const float width = static_cast<float>(max_bx - min_bx), height = static_cast<float>(max_by - min_by);
+    const int n_cols = static_cast<int>(width / 30.f), n_rows = static_cast<int>(height / 30.f);
+    const int w_cell = static_cast<int>(std::ceil(width / n_cols)), h_cell = static_cast<int>(std::ceil(height / n_rows));
+    lv.cell_begin = static_cast<int>(cells_.size());
+    for (int i = 0; i < n_rows; ++i) {
+      const int ini_y = min_by + i * h_cell;
+      int max_y = ini_y + h_cell + 6;
+      if (ini_y >= max_by - 3) continue;
+      if (max_y > max_by) max_y = max_by;
+      for (int j = 0; j < n_cols; ++j) {
+        const int ini_x = min_bx + j * w_cell;
+        int max_x = ini_x + w_cell + 6;
+        if (ini_x >= max_bx - 6) continue;
+        if (max_x > max_bx) max_x = max_bx;
+        OrbCell c;
+        c.level = l;
+        c.x0 = static_cast<short>(ini_x); c.y0 = static_cast<short>(ini_y);
+        c.x1 = static_cast<short>(max_x); c.y1 = static_cast<short>(max_y);
+        cells_.push_back(c);
+      }
+    }
+    lv.cell_end = static_cast<int>(cells_.size());
+  }
+  pyr_bytes_ = img_off;
+  flat_bytes_ = flat_off;
+  const int ncells = static_cast<int>(cells_.size());
+  d_gray_.alloc(static_cast<size_t>(rows) * cols);
+  h_gray_.ensure(static_cast<size_t>(rows) * cols);
+  d_pyr_.alloc(pyr_bytes_);
+  h_pyr_.ensure(pyr_bytes_);
+  d_score_.alloc(flat_bytes_);
+  d_blur_.alloc(flat_bytes_);
+  d_cells_.alloc(std::max<size_t>(1, ncells) * sizeof(OrbCell));
+  if (ncells) SIVO_CUDA(cudaMemcpy(d_cells_.p, cells_.data(), ncells * sizeof(OrbCell), cudaMemcpyHostToDevice));
+  d_cell_count_.alloc(std::max<size_t>(1, ncells) * sizeof(int));
+  d_cell_offset_.alloc((static_cast<size_t>(ncells) + 1) * sizeof(int));
+  d_cell_items_.alloc(std::max<size_t>(1, ncells) * kCellCap * sizeof(uint32_t));
+  cand_cap_ = std::max(32768, nfeatures_ * 16);
+  d_cand_.alloc(static_cast<size_t>(cand_cap_) * sizeof(uint32_t));
+  h_cand_.ensure(static_cast<size_t>(cand_cap_) * sizeof(uint32_t));
+  rows_ = rows;
+  cols_ = cols;
+}
+
+void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypoint* kps, int cap, int* n, uint8_t* desc,
+              uint8_t* const* pyr_out, const size_t* pyr_strides) {
+  if (n) *n = 0;
+  if (!gray || rows <= 0 || cols <= 0) return;  // `if (_image.empty()) return;` (:1023-1024)
+  if (stride < static_cast<size_t>(cols)) fail(SIVO_EINVAL, "ORBextractor: stride smaller than a row");
+  SIVO_CUDA(cudaSetDevice(device_));
+  ensure(rows, cols);
+  const int ncells = static_cast<int>(cells_.size());
+  uint8_t* hg = h_gray_.as<uint8_t>();
+  for (int y = 0; y < rows; ++y) memcpy(hg + static_cast<size_t>(y) * cols, gray + static_cast<size_t>(y) * stride, cols);
+  cudaStream_t s = stream_;
+  SIVO_CUDA(cudaEventRecord(ev_[0], s));
+  SIVO_CUDA(cudaMemcpyAsync(d_gray_.p, hg, static_cast<size_t>(rows) * cols, cudaMemcpyHostToDevice, s));
+  orb_launch_pyramid(d_gray_.as<uint8_t>(), rows, cols, cols, d_pyr_.as<uint8_t>(), lt_, s);
+  orb_launch_score(d_pyr_.as<uint8_t>(), d_score_.as<uint8_t>(), lt_, s);
+  orb_launch_cells(d_score_.as<uint8_t>(), lt_, d_cells_.as<OrbCell>(), ncells, ini_th_, min_th_, d_cell_count_.as<int>(),
+                   d_cell_items_.as<uint32_t>(), s);
+  orb_launch_compact(lt_, d_cells_.as<OrbCell>(), ncells, d_cell_count_.as<int>(), d_cell_items_.as<uint32_t>(),
+                     d_cell_offset_.as<int>(), d_level_off_.as<int>(), d_cand_.as<uint32_t>(), cand_cap_, s);
+  SIVO_CUDA(cudaMemcpyAsync(h_level_off_.p, d_level_off_.p, (nlevels_ + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+  SIVO_CUDA(cudaMemcpyAsync(h_cand_.p, d_cand_.p, static_cast<size_t>(cand_cap_) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  SIVO_CUDA(cudaEventRecord(ev_[1], s));
+  // the blur and the pyramid read-back overlap the host quad tree
+  orb_launch_blur(d_pyr_.as<uint8_t>(), d_blur_.as<uint8_t>(), lt_, s);
+  if (pyr_out) SIVO_CUDA(cudaMemcpyAsync(h_pyr_.p, d_pyr_.p, pyr_bytes_, cudaMemcpyDeviceToHost, s));
+  launches = nlevels_ + 5;
+  SIVO_CUDA(cudaEventSynchronize(ev_[1]));
+
+  const int* loff = h_level_off_.as<int>();
+  const uint32_t* cand = h_cand_.as<uint32_t>();
+  if (loff[nlevels_] > cand_cap_) fail(SIVO_ERANGE, "ORBextractor: %d FAST candidates exceed the workspace (%d)", loff[nlevels_], cand_cap_);
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<sivo_keypoint> out;
+  out.reserve(nfeatures_ + 4 * nlevels_);
+  OrbSelected* sel = h_sel_.as<OrbSelected>();
+  last_cand_.assign(nlevels_, {});
+  std::vector<float> xs, ys, rs;
+  for (int l = 0; l < nlevels_; ++l) {
+    const OrbLevel& lv = lt_.lv[l];
+    const int b = loff[l], e = loff[l + 1], m = e - b;
+    xs.resize(m); ys.resize(m); rs.resize(m);
+    last_cand_[l].resize(static_cast<size_t>(m) * 3);
+    for (int i = 0; i < m; ++i) {
+      uint32_t c = cand[b + i];
+      xs[i] = static_cast<float>(c & 0xFFF);
+      ys[i] = static_cast<float>((c >> 12) & 0xFFF);
+      rs[i] = static_cast<float>(c >> 24);
+      last_cand_[l][3 * i] = c & 0xFFF;
+      last_cand_[l][3 * i + 1] = (c >> 12) & 0xFFF;
+      last_cand_[l][3 * i + 2] = c >> 24;
+    }
+    const int min_b = kEdge - 3;
+    std::vector<int> keep = orb_distribute(xs.data(), ys.data(), rs.data(), m, min_b, lv.w - kEdge + 3, min_b, lv.h - kEdge + 3,
+                                           tab_.per_level[l]);
+    const int scaled_patch = static_cast<int>(31 * tab_.scale[l]);  // PATCH_SIZE * mvScaleFactor[level] (:828)
+    for (int k : keep) {
+      sivo_keypoint kp;
+      kp.x = xs[k] + min_b;
+      kp.y = ys[k] + min_b;
+      kp.size = static_cast<float>(scaled_patch);
+      kp.angle = -1.f;
+      kp.response = rs[k];
+      kp.octave = l;
+      kp.class_id = -1;
+      if (static_cast<int>(out.size()) >= sel_cap_) fail(SIVO_ERANGE, "ORBextractor: more keypoints than the workspace holds");
+      OrbSelected& sk = sel[out.size()];
+      sk.x = static_cast<short>(kp.x); sk.y = static_cast<short>(kp.y); sk.level = static_cast<short>(l); sk.pad = 0;
+      out.push_back(kp);
+    }
+  }
+  tree_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  const int total = static_cast<int>(out.size());
+  SIVO_CUDA(cudaEventRecord(ev_[2], s));
+  if (total) {
+    SIVO_CUDA(cudaMemcpyAsync(d_sel_.p, sel, total * sizeof(OrbSelected), cudaMemcpyHostToDevice, s));
+    orb_launch_describe(d_pyr_.as<uint8_t>(), d_blur_.as<uint8_t>(), lt_, d_sel_.as<OrbSelected>(), total, d_umax_.as<int>(),
+                        d_angles_.as<float>(), d_desc_.as<uint8_t>(), s);
+    SIVO_CUDA(cudaMemcpyAsync(h_angles_.p, d_angles_.p, total * sizeof(float), cudaMemcpyDeviceToHost, s));
+    SIVO_CUDA(cudaMemcpyAsync(h_desc_.p, d_desc_.p, static_cast<size_t>(total) * 32, cudaMemcpyDeviceToHost, s));
+    ++launches;
+  }
+  SIVO_CUDA(cudaEventRecord(ev_[3], s));
+  SIVO_CUDA(cudaStreamSynchronize(s));
+  float a = 0, b2 = 0;
+  SIVO_CUDA(cudaEventElapsedTime(&a, ev_[0], ev_[1]));
+  SIVO_CUDA(cudaEventElapsedTime(&b2, ev_[2], ev_[3]));
+  device_ms = a + b2;
+  if (n) *n = total;
+  if (total > cap) fail(SIVO_ERANGE, "ORBextractor: %d keypoints but the caller's buffers hold %d", total, cap);
+  const float* ang = h_angles_.as<float>();
+  for (int i = 0; i < total; ++i) {
+    sivo_keypoint kp = out[i];
+    kp.angle = ang[i];
+    if (kp.octave != 0) {  // keypoint->pt *= scale (:1071-1078)
+      float sc = tab_.scale[kp.octave];
+      kp.x *= sc;
+      kp.y *= sc;
+    }
+    if (kps) kps[i] = kp;
+  }
+  if (desc && total) memcpy(desc, h_desc_.p, static_cast<size_t>(total) * 32);
+  if (pyr_out) {
+    for (int l = 0; l < nlevels_; ++l) {
+      if (!pyr_out[l]) continue;
+      const OrbLevel& lv = lt_.lv[l];
+      const size_t dst_stride = pyr_strides ? pyr_strides[l] : static_cast<size_t>(lv.w + 2 * kEdge);
+      if (dst_stride < static_cast<size_t>(lv.w + 2 * kEdge)) fail(SIVO_EINVAL, "pyramid stride %zu too small for level %d", dst_stride, l);
+      const uint8_t* src = h_pyr_.as<uint8_t>() + lv.img_off;
+      for (int y = 0; y < lv.h + 2 * kEdge; ++y)
+        memcpy(pyr_out[l] + static_cast<size_t>(y) * dst_stride, src + static_cast<size_t>(y) * lv.pitch, lv.w + 2 * kEdge);
+    }
+  }
+}
+
+void Orb::candidates(int level, int* xs, int* ys, int* resp, int cap, int* n) const {
+  if (level < 0 || level >= static_cast<int>(last_cand_.size())) fail(SIVO_EINVAL, "no candidates for level %d", level);
+  const auto& v = last_cand_[level];
+  int m = static_cast<int>(v.size() / 3);
+  if (n) *n = m;
+  if (m > cap) fail(SIVO_ERANGE, "level %d has %d candidates, buffer holds %d", level, m, cap);
+  for (int i = 0; i < m; ++i) {
+    if (xs) xs[i] = v[3 * i];
+    if (ys) ys[i] = v[3 * i + 1];
+    if (resp) resp[i] = v[3 * i + 2];
+  }
+}
+
+}  // namespace sivo

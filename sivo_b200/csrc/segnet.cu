@@ -1,0 +1,401 @@
+// Host side of the Bayesian SegNet operator: builds the op list from the prototxt (fusing the in-place
+// BN / ReLU followers into their convolution, running everything upstream of the first sampling Dropout
+// once instead of T times) and executes it on one stream.
+#include "segnet.h"
+
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstring>
+
+namespace sivo {
+
+namespace {
+int round_up(int a, int b) { return (a + b - 1) / b * b; }
+float through_half(float x) { return __half2float(__float2half_rn(x)); }
+}  // namespace
+
+int SegNet::add_tensor(const std::string& name, int n, int c, int h, int w, int cs, DType dt, bool mask) {
+  auto t = std::make_unique<Tensor>();
+  t->name = name;
+  t->v.n = n; t->v.c = c; t->v.h = h; t->v.w = w; t->v.cs = cs; t->v.dt = dt;
+  t->is_mask = mask;
+  size_t bytes = mask ? static_cast<size_t>(n) * h * w * cs : t->v.bytes();
+  t->buf.alloc(bytes);
+  t->v.p = t->buf.p;
+  tensors_.push_back(std::move(t));
+  int id = static_cast<int>(tensors_.size()) - 1;
+  by_name_[name] = id;
+  return id;
+}
+
+void SegNet::prepare_conv(Op& op, const std::vector<Blob>& cb, const std::vector<Blob>* bn) {
+  const int K = op.k, cin = op.cin, cout = op.cout;
+  if (cb.empty() || cb[0].shape.size() != 4 || cb[0].shape[0] != cout || cb[0].shape[1] != cin || cb[0].shape[2] != K ||
+      cb[0].shape[3] != K)
+    fail(SIVO_EFORMAT, "layer '%s': weight blob shape does not match (%d,%d,%d,%d) (net.cpp:750-785 would CHECK-fail)",
+         op.layer.c_str(), cout, cin, K, K);
+  const bool half = act_ == DType::F16;
+  const float* W = cb[0].data.data();
+  std::vector<float> ws(static_cast<size_t>(K) * K * op.cin_p * op.cout_p, 0.f);
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int t = 0; t < K * K; ++t) {
+        float v = W[(static_cast<size_t>(co) * cin + ci) * K * K + t];
+        ws[(static_cast<size_t>(t) * op.cin_p + ci) * op.cout_p + co] = half ? through_half(v) : v;
+      }
+  op.w_simt.alloc(ws.size() * sizeof(float));
+  SIVO_CUDA(cudaMemcpy(op.w_simt.p, ws.data(), ws.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (half) {  // tensor-core layout: [tap][cout_p][cin_p] half, K(=cin)-major rows
+    std::vector<__half> wt(static_cast<size_t>(K) * K * op.cout_p * op.cin_p, __float2half_rn(0.f));
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int t = 0; t < K * K; ++t)
+          wt[(static_cast<size_t>(t) * op.cout_p + co) * op.cin_p + ci] =
+              __float2half_rn(W[(static_cast<size_t>(co) * cin + ci) * K * K + t]);
+    op.w_tc.alloc(wt.size() * sizeof(__half));
+    SIVO_CUDA(cudaMemcpy(op.w_tc.p, wt.data(), wt.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  }
+  std::vector<float> b(op.cout_p, 0.f);
+  if (cb.size() > 1) {
+    if (static_cast<int>(cb[1].count()) != cout) fail(SIVO_EFORMAT, "layer '%s': bias blob size mismatch", op.layer.c_str());
+    std::copy(cb[1].data.begin(), cb[1].data.end(), b.begin());
+  }
+  op.bias.alloc(b.size() * sizeof(float));
+  SIVO_CUDA(cudaMemcpy(op.bias.p, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (bn) {
+    if (bn->size() < 2 || static_cast<int>((*bn)[0].count()) != cout || static_cast<int>((*bn)[1].count()) != cout)
+      fail(SIVO_EFORMAT, "BN after '%s': expected scale and shift blobs of %d channels", op.layer.c_str(), cout);
+    std::vector<float> sc(op.cout_p, 1.f), sh(op.cout_p, 0.f);
+    std::copy((*bn)[0].data.begin(), (*bn)[0].data.end(), sc.begin());
+    std::copy((*bn)[1].data.begin(), (*bn)[1].data.end(), sh.begin());
+    op.bn_scale.alloc(sc.size() * sizeof(float));
+    op.bn_shift.alloc(sh.size() * sizeof(float));
+    SIVO_CUDA(cudaMemcpy(op.bn_scale.p, sc.data(), sc.size() * sizeof(float), cudaMemcpyHostToDevice));
+    SIVO_CUDA(cudaMemcpy(op.bn_shift.p, sh.data(), sh.size() * sizeof(float), cudaMemcpyHostToDevice));
+    op.has_bn = true;
+  }
+}
+
+void SegNet::build(const NetSpec& net, const WeightMap& weights) {
+  // consumers of each blob name, to spot the convolution feeding Softmax
+  auto feeds_softmax = [&](size_t li, const std::string& top) {
+    for (size_t j = li + 1; j < net.layers.size(); ++j)
+      for (auto& b : net.layers[j].bottoms)
+        if (b == top) return net.layers[j].type == LayerType::Softmax;
+    return false;
+  };
+  int in_id = add_tensor(net.input_name, 1, 3, H_, W_, 4, act_);
+  {
+    Op op;
+    op.kind = Op::Input;
+    op.layer = "input";
+    op.out = in_id;
+    ops_.push_back(std::move(op));
+  }
+  auto blob_id = [&](const std::string& name) {
+    auto it = by_name_.find(name);
+    if (it == by_name_.end()) fail(SIVO_EFORMAT, "prototxt: blob '%s' is used before it is produced", name.c_str());
+    return it->second;
+  };
+  int drop_idx = 0;
+  bool saw_softmax = false;
+  for (size_t li = 0; li < net.layers.size(); ++li) {
+    const LayerSpec& ly = net.layers[li];
+    if (saw_softmax) fail(SIVO_EFORMAT, "prototxt: layers after Softmax are not on the path");
+    int in = blob_id(ly.bottoms[0]);
+    const TensorView iv = tensors_[in]->v;
+    switch (ly.type) {
+      case LayerType::LRN: {
+        Op op;
+        op.kind = Op::LRN;
+        op.layer = ly.name;
+        op.in = in;
+        op.out = add_tensor(ly.tops[0], iv.n, iv.c, iv.h, iv.w, iv.cs, act_);
+        op.lrn_size = ly.local_size; op.lrn_alpha = ly.alpha; op.lrn_beta = ly.beta; op.lrn_k = ly.k;
+        ops_.push_back(std::move(op));
+        break;
+      }
+      case LayerType::Convolution: {
+        Op op;
+        op.kind = Op::Conv;
+        op.layer = ly.name;
+        op.in = in;
+        op.k = ly.kernel; op.pad = ly.pad; op.cin = iv.c; op.cout = ly.num_output;
+        op.cin_p = iv.cs;
+        op.cout_p = round_up(op.cout, 64);
+        const std::vector<Blob>* bn = nullptr;
+        size_t lj = li + 1;
+        for (; lj < net.layers.size(); ++lj) {  // absorb the in-place followers
+          const LayerSpec& f = net.layers[lj];
+          bool inplace = f.bottoms[0] == ly.tops[0] && f.tops[0] == ly.tops[0];
+          if (!inplace) break;
+          if (f.type == LayerType::BN && !bn && !op.relu) {
+            auto it = weights.find(f.name);
+            if (it == weights.end()) fail(SIVO_EFORMAT, "caffemodel has no blobs for BN layer '%s'", f.name.c_str());
+            bn = &it->second;
+          } else if (f.type == LayerType::ReLU && !op.relu) {
+            op.relu = true;
+            op.slope = f.negative_slope;
+          } else {
+            break;
+          }
+        }
+        bool logits = feeds_softmax(lj - 1, ly.tops[0]);
+        if (!logits && (op.cout % 8)) fail(SIVO_EFORMAT, "layer '%s': %d output channels (need a multiple of 8)", ly.name.c_str(), op.cout);
+        int cs = logits ? round_up(op.cout, 16) : op.cout;
+        op.out = add_tensor(ly.tops[0], iv.n, op.cout, iv.h, iv.w, cs, logits ? DType::F32 : act_);
+        auto it = weights.find(ly.name);
+        if (it == weights.end()) fail(SIVO_EFORMAT, "caffemodel has no blobs for layer '%s'", ly.name.c_str());
+        prepare_conv(op, it->second, bn);
+        op.flops = 2.0 * op.cin * op.k * op.k * op.cout * iv.h * iv.w * iv.n;
+        flops_dedup += op.flops;
+        flops_naive += op.flops / iv.n * T_;
+        if (opt_.engine != SIVO_ENGINE_SIMT && act_ == DType::F16 &&
+            conv_tc_supported(op, iv, tensors_[op.out]->v)) {
+          op.tc = conv_tc_plan(op, iv, tensors_[op.out]->v, op.w_tc.p);
+          op.use_tc = true;
+        } else if (opt_.engine == SIVO_ENGINE_TCGEN05 && op.cin_p % 64 == 0 && !logits) {
+          fail(SIVO_EINVAL, "layer '%s': tcgen05 engine requested but the shape is not supported", ly.name.c_str());
+        }
+        ops_.push_back(std::move(op));
+        li = lj - 1;
+        break;
+      }
+      case LayerType::ReLU:
+      case LayerType::BN:
+        fail(SIVO_EFORMAT, "layer '%s': %s must follow a convolution in place", ly.name.c_str(),
+             ly.type == LayerType::BN ? "BN" : "ReLU");
+      case LayerType::Pooling: {
+        if ((iv.h | iv.w) & 1) fail(SIVO_EFORMAT, "layer '%s': odd input size %dx%d", ly.name.c_str(), iv.h, iv.w);
+        if (iv.cs != iv.c) fail(SIVO_EFORMAT, "layer '%s': pooling a padded-channel tensor", ly.name.c_str());
+        Op op;
+        op.kind = Op::Pool;
+        op.layer = ly.name;
+        op.in = in;
+        op.out = add_tensor(ly.tops[0], iv.n, iv.c, iv.h / 2, iv.w / 2, iv.cs, act_);
+        op.out2 = add_tensor(ly.tops[1], iv.n, iv.c, iv.h / 2, iv.w / 2, iv.cs, act_, true);
+        ops_.push_back(std::move(op));
+        break;
+      }
+      case LayerType::Upsample: {
+        int m = blob_id(ly.bottoms[1]);
+        const Tensor& mt = *tensors_[m];
+        if (!mt.is_mask || mt.v.c != iv.c || mt.v.h != iv.h || mt.v.w != iv.w)
+          fail(SIVO_EFORMAT, "layer '%s': mask blob '%s' does not match the input", ly.name.c_str(), ly.bottoms[1].c_str());
+        Op op;
+        op.kind = Op::Unpool;
+        op.layer = ly.name;
+        op.in = in;
+        op.in2 = m;
+        op.out = add_tensor(ly.tops[0], iv.n, iv.c, iv.h * 2, iv.w * 2, iv.cs, act_);
+        ops_.push_back(std::move(op));
+        break;
+      }
+      case LayerType::Dropout: {
+        if (!ly.sample_weights_test) {  // plain test-time dropout is the identity (dropout_layer.cpp:43-45)
+          by_name_[ly.tops[0]] = in;
+          ++drop_idx;
+          break;
+        }
+        if (ly.dropout_ratio != 0.5f)
+          fail(SIVO_EFORMAT, "layer '%s': dropout_ratio %.3f (the keep-bit rule is specified for 0.5)", ly.name.c_str(), ly.dropout_ratio);
+        Op op;
+        op.kind = Op::Dropout;
+        op.layer = ly.name;
+        op.in = in;
+        op.drop_layer = drop_idx++;
+        op.drop_scale = 1.f / (1.f - ly.dropout_ratio);
+        op.out = add_tensor(ly.tops[0], T_, iv.c, iv.h, iv.w, iv.cs, act_);
+        ops_.push_back(std::move(op));
+        break;
+      }
+      case LayerType::Softmax: {
+        if (iv.dt != DType::F32) fail(SIVO_EFORMAT, "Softmax must follow a convolution");
+        n_classes_ = iv.c;
+        Op op;
+        op.kind = Op::Reduce;
+        op.layer = ly.name;
+        op.in = in;
+        ops_.push_back(std::move(op));
+        saw_softmax = true;
+        break;
+      }
+    }
+  }
+  if (!saw_softmax) fail(SIVO_EFORMAT, "prototxt: no Softmax output layer ('prob')");
+}
+
+SegNet::SegNet(const std::string& prototxt, const std::string& caffemodel, const sivo_segnet_options& opt) : opt_(opt) {
+  // checkConfig (bayesian_segnet.cpp:80-89)
+  if (prototxt.empty()) fail(SIVO_EINVAL, "model_file (.prototxt file) is empty!");
+  if (caffemodel.empty()) fail(SIVO_EINVAL, "weights_file (.caffemodel file) is empty!");
+  NetSpec net = parse_prototxt_file(prototxt);
+  T_ = opt.T > 0 ? opt.T : net.dims[0];
+  // bayesian_segnet.cpp:65-70
+  if (net.dims[1] != 3) fail(SIVO_EINVAL, "Input layer must have 3 channels!");
+  if (T_ <= 1) fail(SIVO_EINVAL, "Input layer must have a batch size greater than 1!");
+  H_ = net.dims[2];
+  W_ = net.dims[3];
+  if (H_ <= 0 || W_ <= 0) fail(SIVO_EFORMAT, "prototxt: bad input geometry %dx%d", W_, H_);
+  act_ = opt.precision == SIVO_PRECISION_FP32 ? DType::F32 : DType::F16;
+  if (opt.precision == SIVO_PRECISION_FP32 && opt.engine == SIVO_ENGINE_TCGEN05)
+    fail(SIVO_EINVAL, "the tcgen05 engine computes on fp16 operands; fp32 precision needs the SIMT engine");
+  WeightMap weights = read_caffemodel(caffemodel);
+  device_ = opt.device;
+  SIVO_CUDA(cudaSetDevice(device_));
+  SIVO_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  d_frame_.alloc(sizeof(uint64_t));
+  h_frame_.ensure(sizeof(uint64_t));
+  build(net, weights);
+  const size_t hw = static_cast<size_t>(H_) * W_;
+  d_bgr_.alloc(hw * 3);
+  d_classes_.alloc(hw);
+  d_conf_.alloc(hw * sizeof(double));
+  d_ent_.alloc(hw * sizeof(double));
+  h_in_.ensure(hw * 3);
+  h_classes_.ensure(hw);
+  h_conf_.ensure(hw * sizeof(double));
+  h_ent_.ensure(hw * sizeof(double));
+  SIVO_CUDA(cudaStreamSynchronize(stream_));
+}
+
+SegNet::~SegNet() {
+  cudaSetDevice(device_);
+  for (auto e : events_) cudaEventDestroy(e);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+void SegNet::run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_dev, double* ent_dev, cudaStream_t s) {
+  SIVO_CUDA(cudaSetDevice(device_));
+  if (!s) s = stream_;
+  *h_frame_.as<uint64_t>() = frame_++;
+  SIVO_CUDA(cudaMemcpyAsync(d_frame_.p, h_frame_.p, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  if (profiling_ && events_.size() < ops_.size() + 1) {
+    while (events_.size() < ops_.size() + 1) {
+      cudaEvent_t e;
+      SIVO_CUDA(cudaEventCreate(&e));
+      events_.push_back(e);
+    }
+  }
+  launches = 0;
+  if (profiling_) SIVO_CUDA(cudaEventRecord(events_[0], s));
+  for (size_t i = 0; i < ops_.size(); ++i) {
+    Op& op = ops_[i];
+    switch (op.kind) {
+      case Op::Input:
+        launch_input_u8(bgr_dev, tensors_[op.out]->v, s);
+        break;
+      case Op::LRN:
+        launch_lrn(tensors_[op.in]->v, tensors_[op.out]->v, op.lrn_size, op.lrn_alpha, op.lrn_beta, op.lrn_k, s);
+        break;
+      case Op::Conv: {
+        if (op.use_tc) {
+          conv_tc_launch(*op.tc, op, s);
+        } else {
+          ConvParams p;
+          p.in = tensors_[op.in]->v;
+          p.out = tensors_[op.out]->v;
+          p.w_simt = op.w_simt.as<float>();
+          p.bias = op.bias.as<float>();
+          p.bn_scale = op.has_bn ? op.bn_scale.as<float>() : nullptr;
+          p.bn_shift = op.has_bn ? op.bn_shift.as<float>() : nullptr;
+          p.k = op.k; p.pad = op.pad; p.cin_p = op.cin_p; p.cout_p = op.cout_p;
+          p.relu = op.relu; p.slope = op.slope;
+          launch_conv_simt(p, s);
+        }
+        break;
+      }
+      case Op::Pool:
+        launch_pool(tensors_[op.in]->v, tensors_[op.out]->v, tensors_[op.out2]->buf.as<uint8_t>(), s);
+        break;
+      case Op::Unpool:
+        launch_unpool(tensors_[op.in]->v, tensors_[op.in2]->buf.as<uint8_t>(), tensors_[op.in2]->v.n, tensors_[op.out]->v, s);
+        break;
+      case Op::Dropout: {
+        DropoutParams d;
+        d.seed = opt_.seed;
+        d.frame_dev = d_frame_.as<uint64_t>();
+        d.layer = op.drop_layer;
+        launch_dropout(tensors_[op.in]->v, tensors_[op.out]->v, d, op.drop_scale, s);
+        break;
+      }
+      case Op::Reduce: {
+        const TensorView& lv = tensors_[op.in]->v;
+        launch_mc_reduce(static_cast<const float*>(lv.p), lv.n, lv.c, lv.cs, lv.h * lv.w, classes_dev, conf_dev, ent_dev, s);
+        break;
+      }
+    }
+    ++launches;
+    if (profiling_) SIVO_CUDA(cudaEventRecord(events_[i + 1], s));
+  }
+  if (profiling_) {
+    SIVO_CUDA(cudaEventSynchronize(events_[ops_.size()]));
+    conv_ms = other_ms = reduce_ms = 0;
+    for (size_t i = 0; i < ops_.size(); ++i) {
+      float ms = 0;
+      SIVO_CUDA(cudaEventElapsedTime(&ms, events_[i], events_[i + 1]));
+      if (ops_[i].kind == Op::Conv) conv_ms += ms;
+      else if (ops_[i].kind == Op::Reduce) reduce_ms += ms;
+      else other_ms += ms;
+    }
+    SIVO_CUDA(cudaEventElapsedTime(&total_ms, events_[0], events_[ops_.size()]));
+  }
+}
+
+void SegNet::run_host(const uint8_t* bgr, int rows, int cols, size_t stride, uint8_t* classes, double* conf, double* ent) {
+  if (!bgr) fail(SIVO_EINVAL, "segmentImage: null image");
+  // resizeImage (bayesian_segnet.cpp:142-162): exact size passes through, larger is centre-cropped;
+  // smaller yields an empty Mat in the reference (and a crash downstream) -- here an error.
+  if (rows < H_ || cols < W_) fail(SIVO_EINVAL, "segmentImage: image %dx%d is smaller than the network input %dx%d", cols, rows, W_, H_);
+  if (stride < static_cast<size_t>(cols) * 3) fail(SIVO_EINVAL, "segmentImage: stride smaller than a row");
+  int x_tl = 0, y_tl = 0;
+  if (rows != H_ || cols != W_) {
+    x_tl = cols / 2 - W_ / 2;
+    y_tl = rows / 2 - H_ / 2;
+  }
+  SIVO_CUDA(cudaSetDevice(device_));
+  uint8_t* stage = h_in_.as<uint8_t>();
+  for (int y = 0; y < H_; ++y)
+    memcpy(stage + static_cast<size_t>(y) * W_ * 3, bgr + static_cast<size_t>(y + y_tl) * stride + static_cast<size_t>(x_tl) * 3,
+           static_cast<size_t>(W_) * 3);
+  const size_t hw = static_cast<size_t>(H_) * W_;
+  SIVO_CUDA(cudaMemcpyAsync(d_bgr_.p, stage, hw * 3, cudaMemcpyHostToDevice, stream_));
+  run_device(d_bgr_.as<uint8_t>(), d_classes_.as<uint8_t>(), d_conf_.as<double>(), d_ent_.as<double>(), stream_);
+  if (classes) SIVO_CUDA(cudaMemcpyAsync(h_classes_.p, d_classes_.p, hw, cudaMemcpyDeviceToHost, stream_));
+  if (conf) SIVO_CUDA(cudaMemcpyAsync(h_conf_.p, d_conf_.p, hw * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  if (ent) SIVO_CUDA(cudaMemcpyAsync(h_ent_.p, d_ent_.p, hw * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  SIVO_CUDA(cudaStreamSynchronize(stream_));
+  // outputs are caller-owned plain memory (Frame copies them into itself, Frame.cc:239-241)
+  if (classes) memcpy(classes, h_classes_.p, hw);
+  if (conf) memcpy(conf, h_conf_.p, hw * sizeof(double));
+  if (ent) memcpy(ent, h_ent_.p, hw * sizeof(double));
+}
+
+void SegNet::blob(const std::string& name, float* out, size_t cap, int* n, int* c, int* h, int* w) {
+  auto it = by_name_.find(name);
+  if (it == by_name_.end()) fail(SIVO_EINVAL, "no blob named '%s'", name.c_str());
+  const Tensor& t = *tensors_[it->second];
+  if (n) *n = t.v.n;
+  if (c) *c = t.v.c;
+  if (h) *h = t.v.h;
+  if (w) *w = t.v.w;
+  if (!out) return;
+  size_t count = static_cast<size_t>(t.v.n) * t.v.c * t.v.h * t.v.w;
+  if (cap < count) fail(SIVO_ERANGE, "blob '%s' has %zu values, buffer holds %zu", name.c_str(), count, cap);
+  SIVO_CUDA(cudaSetDevice(device_));
+  DevBuf tmp(count * sizeof(float));
+  if (t.is_mask) {
+    launch_mask_to_nchw(t.buf.as<uint8_t>(), t.v.n, t.v.c, t.v.h, t.v.w, tmp.as<int>(), stream_);
+    std::vector<int> hi(count);
+    SIVO_CUDA(cudaMemcpyAsync(hi.data(), tmp.p, count * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    SIVO_CUDA(cudaStreamSynchronize(stream_));
+    for (size_t i = 0; i < count; ++i) out[i] = static_cast<float>(hi[i]);  // Caffe stores the index as float
+  } else {
+    launch_act_to_nchw(t.v, tmp.as<float>(), stream_);
+    SIVO_CUDA(cudaMemcpyAsync(out, tmp.p, count * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+    SIVO_CUDA(cudaStreamSynchronize(stream_));
+  }
+}
+
+}  // namespace sivo

@@ -1,0 +1,86 @@
+// Bayesian SegNet executor: prototxt + caffemodel -> a static list of device ops over NHWC tensors.
+// Host-side twin of `SIVO::BayesianSegNet` (src/bayesian_segnet/bayesian_segnet.cpp).
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "caffemodel.h"
+#include "common.h"
+#include "prototxt.h"
+#include "segnet_kernels.h"
+
+namespace sivo {
+
+struct ConvTcPlan;  // conv_tc.cu
+
+struct Tensor {
+  std::string name;
+  TensorView v;
+  DevBuf buf;
+  bool is_mask = false;  // u8 2-bit argmax codes, dims = pooled dims
+};
+
+struct Op {
+  enum Kind { Input, LRN, Conv, Pool, Unpool, Dropout, Reduce } kind = Input;
+  std::string layer;
+  int in = -1, in2 = -1, out = -1, out2 = -1;
+  // LRN
+  int lrn_size = 5;
+  float lrn_alpha = 1.f, lrn_beta = 0.75f, lrn_k = 1.f;
+  // Conv
+  int k = 0, pad = 0, cin = 0, cout = 0, cin_p = 0, cout_p = 0;
+  bool relu = false, has_bn = false;
+  float slope = 0.f;
+  DevBuf w_simt, w_tc, bias, bn_scale, bn_shift;
+  std::shared_ptr<ConvTcPlan> tc;
+  bool use_tc = false;
+  double flops = 0;  // algorithmic, for this op's batch
+  // Dropout
+  int drop_layer = 0;
+  float drop_scale = 2.f;
+};
+
+class SegNet {
+ public:
+  SegNet(const std::string& prototxt, const std::string& caffemodel, const sivo_segnet_options& opt);
+  ~SegNet();
+  int width() const { return W_; }
+  int height() const { return H_; }
+  int T() const { return T_; }
+  int classes() const { return n_classes_; }
+  void set_frame(uint64_t f) { frame_ = f; }
+  void run_host(const uint8_t* bgr, int rows, int cols, size_t stride, uint8_t* classes, double* conf, double* ent);
+  void run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_dev, double* ent_dev, cudaStream_t s);
+  void blob(const std::string& name, float* out, size_t cap, int* n, int* c, int* h, int* w);
+  void set_profiling(bool on) { profiling_ = on; }
+  float conv_ms = 0, other_ms = 0, reduce_ms = 0, total_ms = 0;
+  int launches = 0;
+  double flops_dedup = 0, flops_naive = 0;
+
+ private:
+  int add_tensor(const std::string& name, int n, int c, int h, int w, int cs, DType dt, bool mask = false);
+  void build(const NetSpec& net, const WeightMap& weights);
+  void prepare_conv(Op& op, const std::vector<Blob>& conv_blobs, const std::vector<Blob>* bn_blobs);
+
+  sivo_segnet_options opt_;
+  int device_ = 0, T_ = 0, H_ = 0, W_ = 0, n_classes_ = 0;
+  DType act_ = DType::F16;
+  uint64_t frame_ = 0;
+  bool profiling_ = false;
+  std::vector<std::unique_ptr<Tensor>> tensors_;
+  std::map<std::string, int> by_name_;
+  std::vector<Op> ops_;
+  cudaStream_t stream_ = nullptr;
+  DevBuf d_bgr_, d_classes_, d_conf_, d_ent_, d_frame_;
+  PinnedBuf h_in_, h_classes_, h_conf_, h_ent_, h_frame_;
+  std::vector<cudaEvent_t> events_;
+};
+
+// conv_tc.cu -- tcgen05 implicit-GEMM convolution
+bool conv_tc_supported(const Op& op, const TensorView& in, const TensorView& out);
+std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, const TensorView& out, const void* w_tc);
+void conv_tc_launch(const ConvTcPlan& plan, const Op& op, cudaStream_t s);
+
+}  // namespace sivo

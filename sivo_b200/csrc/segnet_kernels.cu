@@ -1,0 +1,458 @@
+// SegNet layer kernels, SIMT set: the strict-fp32 engine, the correctness anchor for the tcgen05
+// convolution (conv_tc.cu), and every bandwidth-bound layer.  Semantics follow the Caffe layers the
+// reference executes; each kernel cites the layer it replaces.
+#include <cuda_fp16.h>
+
+#include "common.h"
+#include "philox.cuh"
+#include "segnet_kernels.h"
+
+namespace sivo {
+namespace {
+
+template <typename T> __device__ __forceinline__ float ld_act(const T* p);
+template <> __device__ __forceinline__ float ld_act<__half>(const __half* p) { return __half2float(*p); }
+template <> __device__ __forceinline__ float ld_act<float>(const float* p) { return *p; }
+template <typename T> __device__ __forceinline__ void st_act(T* p, float v);
+template <> __device__ __forceinline__ void st_act<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+template <> __device__ __forceinline__ void st_act<float>(float* p, float v) { *p = v; }
+
+// ---- input: wrapInputLayer + preprocessImage (bayesian_segnet.cpp:119-140,164-178): u8 BGR -> float, no
+// mean / scale, planar split.  Here: one NHWC pixel of 4 channels (B, G, R, 0).
+template <typename AT>
+__global__ void k_input_u8(const uint8_t* __restrict__ bgr, AT* __restrict__ out, int npix) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const uint8_t* s = bgr + 3 * static_cast<size_t>(i);
+  AT* d = out + 4 * static_cast<size_t>(i);
+  st_act(d + 0, static_cast<float>(s[0]));
+  st_act(d + 1, static_cast<float>(s[1]));
+  st_act(d + 2, static_cast<float>(s[2]));
+  st_act(d + 3, 0.f);
+}
+
+// ---- LRN across channels (caffe lrn_layer.cpp:108-152): scale = k + alpha/size * sum_{window} x^2,
+// y = x * scale^-beta.  Only ever applied to the 3-channel input, so one thread per pixel.
+template <typename AT>
+__global__ void k_lrn(const AT* __restrict__ in, AT* __restrict__ out, int npix, int c, int cs, int size,
+                      float alpha_over_size, float beta, float k) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const AT* s = in + static_cast<size_t>(i) * cs;
+  AT* d = out + static_cast<size_t>(i) * cs;
+  int pre = (size - 1) / 2;
+  for (int ch = 0; ch < cs; ++ch) {
+    if (ch >= c) { st_act(d + ch, 0.f); continue; }
+    float acc = 0.f;
+    for (int j = ch - pre; j <= ch - pre + size - 1; ++j)
+      if (j >= 0 && j < c) { float x = ld_act(s + j); acc = __fadd_rn(acc, __fmul_rn(x, x)); }
+    float scale = __fadd_rn(k, __fmul_rn(acc, alpha_over_size));
+    st_act(d + ch, __fmul_rn(ld_act(s + ch), powf(scale, -beta)));
+  }
+}
+
+// ---- direct convolution, fp32 FMA (conv_layer.cpp:25-40 / base_conv_layer.cpp:257-280; cuDNN fp32 in the
+// reference's GPU mode).  Block = 8x16 pixels x 64 output channels; thread = 8 pixels of one row x 4 couts.
+// Epilogue order matches the layer sequence: + bias, BN affine (mul then add, bn_layer.cpp:199-223), ReLU.
+constexpr int kTH = 8, kTW = 16, kConvThreads = 256;
+
+template <typename AT, typename OT, int K>
+__global__ void __launch_bounds__(kConvThreads) k_conv_simt(ConvParams p, int CK, int tiles_w) {
+  extern __shared__ float smem[];
+  constexpr int IH = kTH + K - 1, IW = kTW + K - 1, IWP = IW | 1;
+  float* s_w = smem;                          // [K*K][CK][64]
+  float* s_in = smem + K * K * CK * 64;       // [CK][IH][IWP]
+  const int tid = threadIdx.x;
+  const int cg = tid & 15, pg = tid >> 4;
+  const int row = pg >> 1, col0 = (pg & 1) * 8;
+  const int tile_y = blockIdx.x / tiles_w, tile_x = blockIdx.x % tiles_w;
+  const int y0 = tile_y * kTH, x0 = tile_x * kTW;
+  const int co_base = blockIdx.y * 64;
+  const int n = blockIdx.z;
+  const int H = p.in.h, W = p.in.w, cs_in = p.in.cs;
+  const AT* in = static_cast<const AT*>(p.in.p) + static_cast<size_t>(n) * H * W * cs_in;
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int c0 = 0; c0 < p.cin_p; c0 += CK) {
+    for (int e = tid; e < IH * IW * CK; e += kConvThreads) {
+      int ci = e % CK, xy = e / CK;
+      int x = xy % IW, y = xy / IW;
+      int gy = y0 + y - p.pad, gx = x0 + x - p.pad;
+      float v = 0.f;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W && c0 + ci < cs_in)
+        v = ld_act(in + (static_cast<size_t>(gy) * W + gx) * cs_in + c0 + ci);
+      s_in[(ci * IH + y) * IWP + x] = v;
+    }
+    for (int e = tid; e < K * K * CK * 64; e += kConvThreads) {
+      int co = e & 63, r = e >> 6;
+      int ci = r % CK, tap = r / CK;
+      s_w[e] = p.w_simt[(static_cast<size_t>(tap) * p.cin_p + c0 + ci) * p.cout_p + co_base + co];
+    }
+    __syncthreads();
+    for (int ci = 0; ci < CK; ++ci) {
+#pragma unroll
+      for (int kh = 0; kh < K; ++kh) {
+        float xr[8 + K - 1];
+        const float* src = s_in + (ci * IH + row + kh) * IWP + col0;
+#pragma unroll
+        for (int i = 0; i < 8 + K - 1; ++i) xr[i] = src[i];
+#pragma unroll
+        for (int kw = 0; kw < K; ++kw) {
+          const float4 w4 = *reinterpret_cast<const float4*>(s_w + ((kh * K + kw) * CK + ci) * 64 + cg * 4);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            acc[i][0] = fmaf(xr[i + kw], w4.x, acc[i][0]);
+            acc[i][1] = fmaf(xr[i + kw], w4.y, acc[i][1]);
+            acc[i][2] = fmaf(xr[i + kw], w4.z, acc[i][2]);
+            acc[i][3] = fmaf(xr[i + kw], w4.w, acc[i][3]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  const int gy = y0 + row;
+  if (gy >= H) return;
+  OT* out = static_cast<OT*>(p.out.p) + (static_cast<size_t>(n) * H + gy) * W * p.out.cs;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int gx = x0 + col0 + i;
+    if (gx >= W) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int co = co_base + cg * 4 + j;
+      if (co >= p.out.cs) continue;
+      float v = __fadd_rn(acc[i][j], p.bias[co]);
+      if (p.bn_scale) v = __fadd_rn(__fmul_rn(v, p.bn_scale[co]), p.bn_shift[co]);
+      if (p.relu) v = v > 0.f ? v : __fmul_rn(p.slope, v);
+      st_act(out + static_cast<size_t>(gx) * p.out.cs + co, v);
+    }
+  }
+}
+
+// ---- 2x2/2 max pool with argmax (pooling_layer.cpp:140-187): scan (0,0),(0,1),(1,0),(1,1) with strict '>'
+// so the first maximum wins.  The mask is 2 bits (dh*2+dw) per element instead of Caffe's float plane index.
+template <typename AT>
+__global__ void k_pool(const AT* __restrict__ in, AT* __restrict__ out, uint8_t* __restrict__ mask, int N, int Ho,
+                       int Wo, int cs) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t total = static_cast<size_t>(N) * Ho * Wo * cs;
+  if (i >= total) return;
+  int c = i % cs;
+  size_t r = i / cs;
+  int wo = r % Wo;
+  r /= Wo;
+  int ho = r % Ho;
+  int n = r / Ho;
+  int W = Wo * 2;
+  const AT* s = in + ((static_cast<size_t>(n) * Ho * 2 + ho * 2) * W + wo * 2) * cs + c;
+  float best = ld_act(s);
+  int arg = 0;
+  float v = ld_act(s + cs);
+  if (v > best) { best = v; arg = 1; }
+  v = ld_act(s + static_cast<size_t>(W) * cs);
+  if (v > best) { best = v; arg = 2; }
+  v = ld_act(s + static_cast<size_t>(W) * cs + cs);
+  if (v > best) { best = v; arg = 3; }
+  st_act(out + i, best);
+  mask[i] = static_cast<uint8_t>(arg);
+}
+
+// ---- max-unpool (upsample_layer.cpp:74-103): zero fill + scatter, written densely per 2x2 block.
+template <typename AT>
+__global__ void k_unpool(const AT* __restrict__ in, const uint8_t* __restrict__ mask, int mask_n, AT* __restrict__ out,
+                         int N, int Hi, int Wi, int cs) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t total = static_cast<size_t>(N) * Hi * Wi * cs;
+  if (i >= total) return;
+  int c = i % cs;
+  size_t r = i / cs;
+  int wi = r % Wi;
+  r /= Wi;
+  int hi = r % Hi;
+  int n = r / Hi;
+  size_t mi = ((static_cast<size_t>(n % mask_n) * Hi + hi) * Wi + wi) * cs + c;
+  int arg = mask[mi];
+  float v = ld_act(in + i);
+  int W = Wi * 2;
+  AT* d = out + ((static_cast<size_t>(n) * Hi * 2 + hi * 2) * W + wi * 2) * cs + c;
+  st_act(d, arg == 0 ? v : 0.f);
+  st_act(d + cs, arg == 1 ? v : 0.f);
+  st_act(d + static_cast<size_t>(W) * cs, arg == 2 ? v : 0.f);
+  st_act(d + static_cast<size_t>(W) * cs + cs, arg == 3 ? v : 0.f);
+}
+
+// ---- test-time dropout sampling (dropout_layer.cpp:31-46): y = x * keep * 1/(1-ratio).
+template <typename AT>
+__global__ void k_dropout(const AT* __restrict__ in, int in_n, AT* __restrict__ out, int N, int HW, int cs, int C,
+                          uint64_t seed, const uint64_t* __restrict__ frame, int layer, float scale) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // one thread per (n, pix, 32-ch word)
+  int words = (cs + 31) / 32;
+  size_t total = static_cast<size_t>(N) * HW * words;
+  if (i >= total) return;
+  int wd = i % words;
+  size_t r = i / words;
+  uint32_t pix = r % HW;
+  int n = r / HW;
+  uint32_t bits[4];
+  dropout_bits128(seed, *frame, layer, n, pix, wd >> 2, bits);
+  uint32_t b = bits[wd & 3];
+  const AT* s = in + (static_cast<size_t>(n % in_n) * HW + pix) * cs + wd * 32;
+  AT* d = out + (static_cast<size_t>(n) * HW + pix) * cs + wd * 32;
+  int lim = min(32, cs - wd * 32);
+  for (int j = 0; j < lim; ++j) {
+    float v = (wd * 32 + j < C && ((b >> j) & 1u)) ? __fmul_rn(ld_act(s + j), scale) : 0.f;
+    st_act(d + j, v);
+  }
+}
+
+__global__ void k_dropout_bits(uint64_t seed, const uint64_t* frame, int layer, int T, int C, int HW,
+                               uint8_t* __restrict__ keep) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t total = static_cast<size_t>(T) * C * HW;
+  if (i >= total) return;
+  uint32_t pix = i % HW;
+  int c = (i / HW) % C;
+  int n = i / (static_cast<size_t>(HW) * C);
+  uint32_t bits[4];
+  dropout_bits128(seed, *frame, layer, n, pix, c >> 7, bits);
+  keep[i] = (bits[(c >> 5) & 3] >> (c & 31)) & 1u;
+}
+
+// ---- Softmax over channels (softmax_layer.cpp:27-60, fp32) fused with the Monte-Carlo reduction the
+// reference runs on the host in double (bayesian_segnet.cpp:278-318): mean over T, first-max argmax, max,
+// -sum p log2 p with 0 log 0 := 0 (computeEntropy :38-44).  One thread per pixel; `prob` never exists.
+template <int C>
+__global__ void k_mc_reduce(const float* __restrict__ logits, int T, int cs, int hw, uint8_t* __restrict__ classes,
+                            double* __restrict__ conf, double* __restrict__ entropy) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hw) return;
+  double acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.0;
+  for (int t = 0; t < T; ++t) {
+    const float* s = logits + (static_cast<size_t>(t) * hw + i) * cs;
+    float x[C];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { x[c] = s[c]; m = fmaxf(m, x[c]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { x[c] = expf(__fsub_rn(x[c], m)); sum = __fadd_rn(sum, x[c]); }
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] += static_cast<double>(__fdiv_rn(x[c], sum));
+  }
+  double best = -1.0, ent = 0.0;
+  int arg = 0;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    double pm = acc[c] / static_cast<double>(T);
+    if (pm > best) { best = pm; arg = c; }
+    if (pm != 0.0) ent += -1.0 * pm * log2(pm);
+  }
+  if (classes) classes[i] = static_cast<uint8_t>(arg);
+  if (conf) conf[i] = best;
+  if (entropy) entropy[i] = ent;
+}
+
+__global__ void k_mc_reduce_generic(const float* __restrict__ logits, int T, int C, int cs, int hw,
+                                    uint8_t* __restrict__ classes, double* __restrict__ conf,
+                                    double* __restrict__ entropy) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hw) return;
+  double best = -1.0, ent = 0.0;
+  int arg = 0;
+  for (int c = 0; c < C; ++c) {
+    double a = 0.0;
+    for (int t = 0; t < T; ++t) {
+      const float* s = logits + (static_cast<size_t>(t) * hw + i) * cs;
+      float m = -INFINITY;
+      for (int k = 0; k < C; ++k) m = fmaxf(m, s[k]);
+      float sum = 0.f;
+      for (int k = 0; k < C; ++k) sum = __fadd_rn(sum, expf(__fsub_rn(s[k], m)));
+      a += static_cast<double>(__fdiv_rn(expf(__fsub_rn(s[c], m)), sum));
+    }
+    double pm = a / static_cast<double>(T);
+    if (pm > best) { best = pm; arg = c; }
+    if (pm != 0.0) ent += -1.0 * pm * log2(pm);
+  }
+  if (classes) classes[i] = static_cast<uint8_t>(arg);
+  if (conf) conf[i] = best;
+  if (entropy) entropy[i] = ent;
+}
+
+// ---- layout converters for the test hooks
+template <typename AT>
+__global__ void k_nchw_to_act(const float* __restrict__ src, AT* __restrict__ dst, int N, int C, int HW, int cs) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t total = static_cast<size_t>(N) * HW * cs;
+  if (i >= total) return;
+  int c = i % cs;
+  size_t r = i / cs;
+  int pix = r % HW;
+  int n = r / HW;
+  st_act(dst + i, c < C ? src[(static_cast<size_t>(n) * C + c) * HW + pix] : 0.f);
+}
+template <typename AT>
+__global__ void k_act_to_nchw(const AT* __restrict__ src, float* __restrict__ dst, int N, int C, int HW, int cs) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t total = static_cast<size_t>(N) * C * HW;
+  if (i >= total) return;
+  int pix = i % HW;
+  int c = (i / HW) % C;
+  int n = i / (static_cast<size_t>(HW) * C);
+  dst[i] = ld_act(src + (static_cast<size_t>(n) * HW + pix) * cs + c);
+}
+// 2-bit mask <-> Caffe's plane-local index h*W+w of the *input* plane (pooling_layer.cpp:168)
+__global__ void k_mask_to_nchw(const uint8_t* __restrict__ mask, int N, int C, int Ho, int Wo, int* __restrict__ dst) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t total = static_cast<size_t>(N) * C * Ho * Wo;
+  if (i >= total) return;
+  int wo = i % Wo;
+  int ho = (i / Wo) % Ho;
+  int c = (i / (static_cast<size_t>(Wo) * Ho)) % C;
+  int n = i / (static_cast<size_t>(Wo) * Ho * C);
+  int a = mask[((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C + c];
+  dst[i] = (ho * 2 + (a >> 1)) * (Wo * 2) + wo * 2 + (a & 1);
+}
+__global__ void k_mask_from_nchw(const int* __restrict__ src, int N, int C, int Ho, int Wo, uint8_t* __restrict__ mask) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t total = static_cast<size_t>(N) * C * Ho * Wo;
+  if (i >= total) return;
+  int wo = i % Wo;
+  int ho = (i / Wo) % Ho;
+  int c = (i / (static_cast<size_t>(Wo) * Ho)) % C;
+  int n = i / (static_cast<size_t>(Wo) * Ho * C);
+  int idx = src[i];
+  int y = idx / (Wo * 2), x = idx % (Wo * 2);
+  mask[((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C + c] = static_cast<uint8_t>(((y - ho * 2) << 1) | (x - wo * 2));
+}
+
+inline unsigned blocks_for(size_t total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
+
+template <typename AT, typename OT>
+void conv_dispatch(const ConvParams& p, cudaStream_t s) {
+  int tiles_w = ceil_div(p.in.w, kTW), tiles_h = ceil_div(p.in.h, kTH);
+  dim3 grid(tiles_w * tiles_h, p.cout_p / 64, p.in.n);
+  auto go = [&](auto kern, int K, int CK) {
+    int IH = kTH + K - 1, IW = kTW + K - 1, IWP = IW | 1;
+    size_t smem = (static_cast<size_t>(K) * K * CK * 64 + static_cast<size_t>(CK) * IH * IWP) * sizeof(float);
+    SIVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, kConvThreads, smem, s>>>(p, CK, tiles_w);
+    SIVO_CUDA(cudaGetLastError());
+  };
+  auto pick_ck = [&](int want) {
+    int ck = want;
+    while (p.cin_p % ck) ck >>= 1;
+    return ck;
+  };
+  switch (p.k) {
+    case 1: go(k_conv_simt<AT, OT, 1>, 1, pick_ck(16)); break;
+    case 3: go(k_conv_simt<AT, OT, 3>, 3, pick_ck(16)); break;
+    case 5: go(k_conv_simt<AT, OT, 5>, 5, pick_ck(8)); break;
+    case 7: go(k_conv_simt<AT, OT, 7>, 7, pick_ck(4)); break;
+    default: fail(SIVO_EFORMAT, "convolution kernel size %d is not supported (1, 3, 5, 7)", p.k);
+  }
+}
+
+}  // namespace
+
+#define DISPATCH_AT(dt, ...)                              \
+  do {                                                    \
+    if ((dt) == DType::F16) { using AT = __half; __VA_ARGS__; } \
+    else { using AT = float; __VA_ARGS__; }               \
+  } while (0)
+
+void launch_input_u8(const uint8_t* bgr, TensorView out, cudaStream_t s) {
+  int npix = out.h * out.w;
+  DISPATCH_AT(out.dt, (k_input_u8<AT><<<blocks_for(npix, 256), 256, 0, s>>>(bgr, static_cast<AT*>(out.p), npix)));
+  SIVO_CUDA(cudaGetLastError());
+}
+
+void launch_lrn(TensorView in, TensorView out, int size, float alpha, float beta, float k, cudaStream_t s) {
+  int npix = in.n * in.h * in.w;
+  float aos = alpha / static_cast<float>(size);
+  DISPATCH_AT(in.dt, (k_lrn<AT><<<blocks_for(npix, 256), 256, 0, s>>>(static_cast<const AT*>(in.p), static_cast<AT*>(out.p),
+                                                                      npix, in.c, in.cs, size, aos, beta, k)));
+  SIVO_CUDA(cudaGetLastError());
+}
+
+void launch_conv_simt(const ConvParams& p, cudaStream_t s) {
+  if (p.in.dt == DType::F16) {
+    if (p.out.dt == DType::F16) conv_dispatch<__half, __half>(p, s);
+    else conv_dispatch<__half, float>(p, s);
+  } else {
+    conv_dispatch<float, float>(p, s);
+  }
+}
+
+void launch_pool(TensorView in, TensorView out, uint8_t* mask, cudaStream_t s) {
+  size_t total = out.elems();
+  DISPATCH_AT(in.dt, (k_pool<AT><<<blocks_for(total, 256), 256, 0, s>>>(static_cast<const AT*>(in.p), static_cast<AT*>(out.p),
+                                                                        mask, out.n, out.h, out.w, out.cs)));
+  SIVO_CUDA(cudaGetLastError());
+}
+
+void launch_unpool(TensorView in, const uint8_t* mask, int mask_n, TensorView out, cudaStream_t s) {
+  size_t total = in.elems();
+  DISPATCH_AT(in.dt, (k_unpool<AT><<<blocks_for(total, 256), 256, 0, s>>>(static_cast<const AT*>(in.p), mask, mask_n,
+                                                                          static_cast<AT*>(out.p), in.n, in.h, in.w, in.cs)));
+  SIVO_CUDA(cudaGetLastError());
+}
+
+void launch_dropout(TensorView in, TensorView out, const DropoutParams& d, float scale, cudaStream_t s) {
+  int words = (out.cs + 31) / 32;
+  size_t total = static_cast<size_t>(out.n) * out.h * out.w * words;
+  DISPATCH_AT(in.dt, (k_dropout<AT><<<blocks_for(total, 256), 256, 0, s>>>(static_cast<const AT*>(in.p), in.n,
+                                                                           static_cast<AT*>(out.p), out.n, out.h * out.w,
+                                                                           out.cs, out.c, d.seed, d.frame_dev, d.layer, scale)));
+  SIVO_CUDA(cudaGetLastError());
+}
+
+void launch_mc_reduce(const float* logits, int T, int C, int cs, int hw, uint8_t* classes, double* conf, double* entropy,
+                      cudaStream_t s) {
+  if (C == 15) k_mc_reduce<15><<<blocks_for(hw, 128), 128, 0, s>>>(logits, T, cs, hw, classes, conf, entropy);
+  else k_mc_reduce_generic<<<blocks_for(hw, 128), 128, 0, s>>>(logits, T, C, cs, hw, classes, conf, entropy);
+  SIVO_CUDA(cudaGetLastError());
+}
+
+void launch_dropout_bits(uint64_t seed, const uint64_t* frame_dev, int layer, int T, int C, int H, int W, uint8_t* keep,
+                         cudaStream_t s) {
+  size_t total = static_cast<size_t>(T) * C * H * W;
+  k_dropout_bits<<<blocks_for(total, 256), 256, 0, s>>>(seed, frame_dev, layer, T, C, H * W, keep);
+  SIVO_CUDA(cudaGetLastError());
+}
+
+void launch_nchw_to_act(const float* src, TensorView dst, cudaStream_t s) {
+  size_t total = dst.elems();
+  DISPATCH_AT(dst.dt, (k_nchw_to_act<AT><<<blocks_for(total, 256), 256, 0, s>>>(src, static_cast<AT*>(dst.p), dst.n, dst.c,
+                                                                               dst.h * dst.w, dst.cs)));
+  SIVO_CUDA(cudaGetLastError());
+}
+
+void launch_act_to_nchw(TensorView src, float* dst, cudaStream_t s) {
+  size_t total = static_cast<size_t>(src.n) * src.c * src.h * src.w;
+  DISPATCH_AT(src.dt, (k_act_to_nchw<AT><<<blocks_for(total, 256), 256, 0, s>>>(static_cast<const AT*>(src.p), dst, src.n,
+                                                                               src.c, src.h * src.w, src.cs)));
+  SIVO_CUDA(cudaGetLastError());
+}
+
+void launch_mask_to_nchw(const uint8_t* mask, int n, int c, int ho, int wo, int* dst, cudaStream_t s) {
+  size_t total = static_cast<size_t>(n) * c * ho * wo;
+  k_mask_to_nchw<<<blocks_for(total, 256), 256, 0, s>>>(mask, n, c, ho, wo, dst);
+  SIVO_CUDA(cudaGetLastError());
+}
+
+void launch_mask_from_nchw(const int* src, int n, int c, int ho, int wo, uint8_t* mask, cudaStream_t s) {
+  size_t total = static_cast<size_t>(n) * c * ho * wo;
+  k_mask_from_nchw<<<blocks_for(total, 256), 256, 0, s>>>(src, n, c, ho, wo, mask);
+  SIVO_CUDA(cudaGetLastError());
+}
+
+}  // namespace sivo

@@ -1,0 +1,58 @@
+// Launch wrappers of the SegNet layer kernels.  Activations are NHWC ("pixel-major": the channel
+// vector of one pixel is contiguous) in half (default) or float (strict mode); `cs` is the channel
+// stride in elements (4 for the 3-channel input, 16 for the 15 logits, C otherwise).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace sivo {
+
+enum class DType : int { F16 = 0, F32 = 1 };
+inline size_t dtype_size(DType t) { return t == DType::F16 ? 2 : 4; }
+
+struct TensorView {
+  void* p = nullptr;
+  int n = 0, c = 0, h = 0, w = 0, cs = 0;
+  DType dt = DType::F16;
+  size_t elems() const { return static_cast<size_t>(n) * h * w * cs; }
+  size_t bytes() const { return elems() * dtype_size(dt); }
+};
+
+struct ConvParams {
+  TensorView in, out;
+  const float* w_simt = nullptr;   // [k*k][cin_p][cout_p] float
+  const float* bias = nullptr;     // [cout_p]
+  const float* bn_scale = nullptr; // [cout_p] or null
+  const float* bn_shift = nullptr;
+  int k = 0, pad = 0, cin_p = 0, cout_p = 0;
+  int relu = 0;
+  float slope = 0.f;
+};
+
+struct DropoutParams {
+  uint64_t seed = 0;
+  const uint64_t* frame_dev = nullptr;  // device scalar, so a captured graph replays with a new frame
+  int layer = 0;
+};
+
+void launch_input_u8(const uint8_t* bgr_hwc, TensorView out, cudaStream_t s);
+void launch_lrn(TensorView in, TensorView out, int size, float alpha, float beta, float k, cudaStream_t s);
+void launch_conv_simt(const ConvParams& p, cudaStream_t s);
+void launch_pool(TensorView in, TensorView out, uint8_t* mask, cudaStream_t s);
+// mask_n: batch of the mask tensor (1 when the pool ran in the sample-invariant prefix)
+void launch_unpool(TensorView in, const uint8_t* mask, int mask_n, TensorView out, cudaStream_t s);
+// in.n may be 1 (broadcast to out.n samples)
+void launch_dropout(TensorView in, TensorView out, const DropoutParams& d, float scale, cudaStream_t s);
+// logits: float [T, H, W, 16]
+void launch_mc_reduce(const float* logits, int T, int C, int cs, int hw, uint8_t* classes, double* conf,
+                      double* entropy, cudaStream_t s);
+void launch_dropout_bits(uint64_t seed, const uint64_t* frame_dev, int layer, int T, int C, int H, int W,
+                         uint8_t* keep_nchw, cudaStream_t s);
+// layout converters for the test hooks (float NCHW host order <-> NHWC activation)
+void launch_nchw_to_act(const float* src, TensorView dst, cudaStream_t s);
+void launch_act_to_nchw(TensorView src, float* dst, cudaStream_t s);
+void launch_mask_to_nchw(const uint8_t* mask, int n, int c, int ho, int wo, int* dst, cudaStream_t s);
+void launch_mask_from_nchw(const int* src, int n, int c, int ho, int wo, uint8_t* mask, cudaStream_t s);
+
+}  // namespace sivo

@@ -1,0 +1,116 @@
+"""Python mirror of `SIVO::ORBextractor` (include/orbslam/ORBextractor.h:46-125) and of the Hamming stage
+of `Frame::ComputeStereoMatches` over the C-ABI."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib as L
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+
+
+class ORBextractor:
+    def __init__(self, nfeatures: int, scaleFactor: float, nlevels: int, iniThFAST: int, minThFAST: int, device: int = 0):
+        self._h = C.c_void_p()
+        L.check(L.lib().sivo_orb_create(nfeatures, C.c_float(scaleFactor), nlevels, iniThFAST, minThFAST, device,
+                                        C.byref(self._h)))
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self._scale = np.empty(nlevels, np.float32)
+        self._inv = np.empty(nlevels, np.float32)
+        self._s2 = np.empty(nlevels, np.float32)
+        self._is2 = np.empty(nlevels, np.float32)
+        self._per = np.empty(nlevels, np.int32)
+        L.check(L.lib().sivo_orb_tables(self._h, *(a.ctypes.data_as(C.c_void_p) for a in
+                                                   (self._scale, self._inv, self._s2, self._is2, self._per))))
+        self.mvImagePyramid: List[np.ndarray] = []
+        self._scale_factor = scaleFactor
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            L.lib().sivo_orb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def GetLevels(self): return self.nlevels
+    def GetScaleFactor(self): return float(np.float32(self._scale_factor))
+    def GetScaleFactors(self): return self._scale.copy()
+    def GetInverseScaleFactors(self): return self._inv.copy()
+    def GetScaleSigmaSquares(self): return self._s2.copy()
+    def GetInverseScaleSigmaSquares(self): return self._is2.copy()
+    def features_per_level(self): return self._per.copy()
+
+    def __call__(self, image: np.ndarray, mask=None, want_pyramid: bool = True):
+        """Returns (keypoints structured array KP_DTYPE, descriptors u8 [N,32]); fills mvImagePyramid with
+        views at offset (19,19) into the bordered level buffers, like the reference's public member."""
+        if image is None or image.size == 0:
+            return np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise ValueError("ORBextractor expects a single-channel uint8 image")  # assert(type == CV_8UC1)
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        rows, cols = image.shape
+        cap = self.nfeatures + 4 * self.nlevels + 64
+        kps = np.empty(cap, KP_DTYPE)
+        desc = np.empty((cap, 32), np.uint8)
+        n = C.c_int(0)
+        ptrs = strides = None
+        bufs = []
+        if want_pyramid:
+            ptrs = (C.c_void_p * self.nlevels)()
+            strides = (C.c_size_t * self.nlevels)()
+            for l in range(self.nlevels):
+                w, h = C.c_int(), C.c_int()
+                L.check(L.lib().sivo_orb_level_size(self._h, rows, cols, l, C.byref(w), C.byref(h)))
+                b = np.empty((h.value + 38, w.value + 38), np.uint8)
+                bufs.append(b)
+                ptrs[l] = b.ctypes.data
+                strides[l] = b.strides[0]
+        L.check(L.lib().sivo_orb_run(self._h, image.ctypes.data_as(C.c_void_p), rows, cols, C.c_size_t(image.strides[0]),
+                                     kps.ctypes.data_as(C.c_void_p), cap, C.byref(n), desc.ctypes.data_as(C.c_void_p),
+                                     ptrs, strides))
+        self._bordered = bufs
+        self.mvImagePyramid = [b[19:-19, 19:-19] for b in bufs]
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def candidates(self, level: int):
+        n = C.c_int()
+        cap = 1 << 16
+        xs, ys, rs = (np.empty(cap, np.int32) for _ in range(3))
+        L.check(L.lib().sivo_orb_candidates(self._h, level, xs.ctypes.data_as(C.c_void_p), ys.ctypes.data_as(C.c_void_p),
+                                            rs.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
+        return xs[:n.value].copy(), ys[:n.value].copy(), rs[:n.value].copy()
+
+    def last_timing(self):
+        a, b, n = C.c_float(), C.c_float(), C.c_int()
+        L.check(L.lib().sivo_orb_last_timing(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return {"device_ms": a.value, "tree_ms": b.value, "launches": n.value}
+
+
+def distribute_octtree(xs, ys, resp, min_x, max_x, min_y, max_y, n_target) -> np.ndarray:
+    """Host-only DistributeOctTree of the library (no GPU needed)."""
+    xs = np.ascontiguousarray(xs, np.float32)
+    ys = np.ascontiguousarray(ys, np.float32)
+    resp = np.ascontiguousarray(resp, np.float32)
+    keep = np.empty(max(len(xs), 1), np.int32)
+    n = L.check(L.lib().sivo_orb_distribute(xs.ctypes.data_as(C.c_void_p), ys.ctypes.data_as(C.c_void_p),
+                                            resp.ctypes.data_as(C.c_void_p), len(xs), min_x, max_x, min_y, max_y, n_target,
+                                            keep.ctypes.data_as(C.c_void_p), len(keep)))
+    return keep[:n].copy()
+
+
+def stereo_hamming(kp_left, desc_left, kp_right, desc_right, scale_factors, rows, min_d, max_d, device: int = 0):
+    kl = np.ascontiguousarray(kp_left, KP_DTYPE)
+    kr = np.ascontiguousarray(kp_right, KP_DTYPE)
+    dl = np.ascontiguousarray(desc_left, np.uint8)
+    dr = np.ascontiguousarray(desc_right, np.uint8)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    idx = np.empty(len(kl), np.int32)
+    dist = np.empty(len(kl), np.int32)
+    L.check(L.lib().sivo_stereo_hamming(device, kl.ctypes.data_as(C.c_void_p), dl.ctypes.data_as(C.c_void_p), len(kl),
+                                        kr.ctypes.data_as(C.c_void_p), dr.ctypes.data_as(C.c_void_p), len(kr),
+                                        sf.ctypes.data_as(C.c_void_p), len(sf), rows, C.c_float(min_d), C.c_float(max_d),
+                                        idx.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p)))
+    return idx, dist
