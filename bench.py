@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Headline benchmark: frames/sec of the SIVO perception front-end -- Bayesian SegNet(T) on the left image plus
+the ORB extractor on the left and right images -- on synthetic 1242x375 stereo frames (centre-cropped to the
+net's 1024x352 like System::TrackStereo does), N x B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model basic|standard] [--T 6]
+
+One "step" = one stereo frame through both operators.  `value` times the operators with the cropped inputs
+already resident in HBM; `e2e` times the reference-facing calls (segmentImage / operator()) on HOST buffers,
+host<->device copies included, left/right ORB on two threads as Frame.cc:126-129 does.  N > 1 shards frames
+one per rank (weak scaling) and all-gathers a packed per-frame record over NCCL each step.
+`--impl reference` times the CPU restatement of the reference path (oracle/) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+CROP_X, CROP_Y, NET_W, NET_H = 109, 11, 1024, 352
+BASELINE_PUBLISHED = None  # BASELINE.md holds no published number for this metric
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="basic", choices=["basic", "standard"])
+    ap.add_argument("--T", type=int, default=0, help="MC samples (default 6 basic / 12 standard; 6 standard for N>1)")
+    ap.add_argument("--nfeatures", type=int, default=2000)
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def model_files(kind, T, cache_dir):
+    """Prototxt + seeded synthetic caffemodel (the reference's weights are Git-LFS stubs)."""
+    import gen_prototxt
+    from sivo_b200.caffemodel import write_synth_model
+    from sivo_b200.prototxt import load_net
+    os.makedirs(cache_dir, exist_ok=True)
+    text = getattr(gen_prototxt, kind)(T=T)
+    proto = os.path.join(cache_dir, f"{kind}_T{T}.prototxt")
+    model = os.path.join(cache_dir, f"{kind}_seed0.caffemodel")
+    with open(proto, "w") as f:
+        f.write(text)
+    net = load_net(text)
+    weights = None
+    if not os.path.exists(model):
+        weights = write_synth_model(net, model, 0)
+    return net, proto, model, weights
+
+
+def frames(n, start=0):
+    from sivo_b200.synth import bgr_to_gray, stereo_frame
+    out = []
+    for i in range(n):
+        left, right = stereo_frame(start + i)
+        gl = np.ascontiguousarray(bgr_to_gray(left)[CROP_Y:CROP_Y + NET_H, CROP_X:CROP_X + NET_W])
+        gr = np.ascontiguousarray(bgr_to_gray(right)[CROP_Y:CROP_Y + NET_H, CROP_X:CROP_X + NET_W])
+        out.append((left, gl, gr))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_reference_frame(net, weights, left_bgr, gl, gr, nfeatures, threads):
+    """One frame of the CPU restatement of the reference path: SegNet(T) (torch fp32, all host threads) then
+    the OpenCV-composed ORB extractor on two threads (Frame.cc:125-129 order)."""
+    from oracle import orb_cv2, segnet_oracle as S
+    t0 = time.perf_counter()
+    S.segment_image(net, weights, left_bgr, seed=1234, frame=0, precision="fp32", threads=threads)
+    t1 = time.perf_counter()
+    th = [threading.Thread(target=orb_cv2.extract, args=(g, nfeatures)) for g in (gl, gr)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def load_weights(net, model):
+    from sivo_b200.caffemodel import read_caffemodel
+    return read_caffemodel(model)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    T = args.T or (6 if args.model == "basic" else 12)
+    net, proto, model, weights = model_files(args.model, T, os.path.join("/tmp", "sivo_b200_models"))
+    weights = weights or load_weights(net, model)
+    cores = os.cpu_count() or 1
+    fr = frames(1)
+    times = []
+    for i in range(args.warmup + args.steps):
+        a, b = cpu_reference_frame(net, weights, fr[0][0], fr[0][1], fr[0][2], args.nfeatures, cores)
+        if i >= args.warmup:
+            times.append(a + b)
+        if sum(times) > 240 and len(times) >= 1:  # bounded: keep the arm within a few minutes
+            break
+    ms = 1e3 * float(np.mean(times))
+    fps = 1e3 / ms
+    line = {"impl": "reference", "metric": "frames/sec SegNet(T)+ORB", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, T),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{len(times)} full frame(s): SegNet {args.model} T={T} (torch-CPU fp32 restatement) + ORB({args.nfeatures}) x2 (cv2 composition)"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, T):
+    return {"workload": f"Bayesian SegNet {args.model.capitalize()} T={T} + ORB({args.nfeatures}) x2, synthetic 1242x375 stereo "
+                        f"(centre-cropped to 1024x352), one frame per GPU",
+            "model": args.model, "T": T, "nfeatures": args.nfeatures, "engine": args.engine, "precision": args.precision,
+            "l2": "inputs+activations per frame (>300 MB) exceed the 126 MB L2; distinct frame each step"}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    from sivo_b200 import BayesianSegNet, BayesianSegNetParams, ORBextractor
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    T = args.T or (6 if args.model == "basic" else (12 if world == 1 else 6))
+    cache = os.path.join("/tmp", "sivo_b200_models")
+    if rank == 0:
+        net, proto, model, weights = model_files(args.model, T, cache)
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        net, proto, model, weights = model_files(args.model, T, cache)
+
+    seg = BayesianSegNet(BayesianSegNetParams(proto, model), device=local_rank, seed=1234, precision=args.precision,
+                         engine=args.engine)
+    orb_l = ORBextractor(args.nfeatures, 1.2, 8, 20, 7, device=local_rank)
+    orb_r = ORBextractor(args.nfeatures, 1.2, 8, 20, 7, device=local_rank)
+    n_frames = 8
+    fr = frames(n_frames, start=rank * n_frames)
+    hw = NET_H * NET_W
+    # ---- device-resident inputs for `value`
+    d_bgr = [torch.from_numpy(np.ascontiguousarray(f[0][CROP_Y:CROP_Y + NET_H, CROP_X:CROP_X + NET_W])).to(dev) for f in fr]
+    d_gl = [torch.from_numpy(f[1]).to(dev) for f in fr]
+    d_gr = [torch.from_numpy(f[2]).to(dev) for f in fr]
+    d_cls = torch.empty(hw, dtype=torch.uint8, device=dev)
+    d_conf = torch.empty(hw, dtype=torch.float64, device=dev)
+    d_ent = torch.empty(hw, dtype=torch.float64, device=dev)
+    # packed per-frame record for the N>1 all-gather: classes u8 | conf f64 | entropy f64 | 2 x (count, kps, desc)
+    kp_cap = args.nfeatures + 4 * 8 + 64
+    rec_bytes = hw * 17 + 2 * (8 + kp_cap * 60)
+    rec_bytes = (rec_bytes + 255) // 256 * 256
+    d_rec = torch.zeros(rec_bytes, dtype=torch.uint8, device=dev)
+    d_all = torch.empty(rec_bytes * world, dtype=torch.uint8, device=dev) if world > 1 else None
+    h_kp = torch.empty(2 * (8 + kp_cap * 60), dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+
+    def pack_keypoints(kl, dl, kr, dr):
+        buf = h_kp.numpy()
+        off = 0
+        for k, d in ((kl, dl), (kr, dr)):
+            n = len(k)
+            buf[off:off + 8] = np.frombuffer(np.int64(n).tobytes(), np.uint8)
+            buf[off + 8:off + 8 + n * 28] = k.view(np.uint8).reshape(-1)[:n * 28]
+            buf[off + 8 + kp_cap * 28:off + 8 + kp_cap * 28 + n * 32] = d.reshape(-1)
+            off += 8 + kp_cap * 60
+
+    def device_step(i):
+        j = i % n_frames
+        seg.run_device(d_bgr[j].data_ptr(), d_cls.data_ptr(), d_conf.data_ptr(), d_ent.data_ptr(), stream.cuda_stream)
+        out = [None, None]
+
+        def right():
+            out[1] = orb_r.run_device_input(d_gr[j].data_ptr(), NET_H, NET_W, NET_W)
+        t = threading.Thread(target=right)
+        t.start()
+        out[0] = orb_l.run_device_input(d_gl[j].data_ptr(), NET_H, NET_W, NET_W)
+        t.join()
+        if world > 1:
+            pack_keypoints(out[0][0], out[0][1], out[1][0], out[1][1])
+            d_rec[:hw].copy_(d_cls, non_blocking=True)
+            d_rec[hw:hw * 9].copy_(d_conf.view(torch.uint8), non_blocking=True)
+            d_rec[hw * 9:hw * 17].copy_(d_ent.view(torch.uint8), non_blocking=True)
+            d_rec[hw * 17:hw * 17 + h_kp.numel()].copy_(h_kp, non_blocking=True)
+            dist.all_gather_into_tensor(d_all, d_rec)
+        return out
+
+    def host_step(i):
+        j = i % n_frames
+        left, gl, gr = fr[j]
+        res = seg.segmentImage(left)  # host image in, host maps out (H2D + D2H inside)
+        out = [None, None]
+
+        def right():
+            out[1] = orb_r(gr, None, want_pyramid=True)
+        t = threading.Thread(target=right)
+        t.start()
+        out[0] = orb_l(gl, None, want_pyramid=True)
+        t.join()
+        return res, out
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- value: inputs resident in HBM
+    for i in range(args.warmup):
+        device_step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t0 = time.perf_counter()
+    launches = 0
+    for i in range(args.steps):
+        device_step(args.warmup + i)
+        launches += seg.last_timing()["launches"] + orb_l.last_timing()["launches"] + orb_r.last_timing()["launches"]
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
+    elapsed = max(wall, dev_ms / 1e3)  # the ORB streams are the library's own; wall brackets everything (synced both sides)
+    # ---- e2e: host buffers through the operator calls
+    for i in range(max(2, args.warmup // 2)):
+        host_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        res, out = host_step(args.warmup + i)
+    barrier()
+    e2e_elapsed = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    n_kp = len(out[0][0]) + len(out[1][0])
+    h2d = 1242 * 375 * 0 + hw * 3 + 2 * hw + n_kp * 8
+    d2h = hw * 17 + n_kp * 36 + 2 * (32768 * 4 + 9 * 4) + 2 * sum((int(round(NET_H / 1.2 ** l)) + 38) * (int(round(NET_W / 1.2 ** l)) + 38 + 15) for l in range(8))
+    if world > 1:
+        tt = torch.tensor([elapsed, e2e_elapsed], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed, e2e_elapsed = float(tt[0]), float(tt[1])
+
+    # ---- roofline of the dominant kernel: per-op CUDA events on the launching stream (profiling pass)
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        seg.set_profiling(True)
+        conv_ms, tot_ms = [], []
+        for i in range(min(args.steps, 10)):
+            seg.run_device(d_bgr[i % n_frames].data_ptr(), d_cls.data_ptr(), d_conf.data_ptr(), d_ent.data_ptr(), stream.cuda_stream)
+            tm = seg.last_timing()
+            conv_ms.append(tm["conv_ms"])
+            tot_ms.append(tm["total_ms"])
+        seg.set_profiling(False)
+        fl = seg.flops()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained") or 1400.0
+        which = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF sustained (B200_PROFILING.md)"
+        ach = fl["dedup"] / (np.mean(conv_ms) * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "kernel": "convolution layers (all conv launches of one frame)", "peak_source": which,
+                "conv_ms_per_frame": float(np.mean(conv_ms)), "segnet_ms_per_frame": float(np.mean(tot_ms)),
+                "algorithmic_gflop_per_frame": fl["dedup"] / 1e9, "naive_gflop_per_frame": fl["naive"] / 1e9}
+        if not args.no_cpu_baseline and world == 1:
+            w = weights or load_weights(net, model)
+            cores = os.cpu_count() or 1
+            a, b = cpu_reference_frame(net, w, fr[0][0], fr[0][1], fr[0][2], args.nfeatures, cores)
+            cpu_base = {"value": 1.0 / (a + b), "unit": "frames/s", "cores": cores, "kind": "port",
+                        "sample": f"1 full frame: SegNet {args.model} T={T} torch-CPU fp32 restatement ({a:.2f} s) + ORB({args.nfeatures}) x2 cv2 composition ({b:.2f} s)"}
+    if rank == 0:
+        total_frames = args.steps * world
+        fps = total_frames / elapsed
+        line = {"metric": "frames/sec SegNet(T)+ORB", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "f32", "data": "synthetic",
+                "config": workload_config(args, T), "clocks": clocks,
+                "e2e": {"value": total_frames / e2e_elapsed, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu_base,
+                "keypoints_last_frame": int(n_kp)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -107,6 +107,10 @@ int sivo_orb_tables(const sivo_orb_t* h, float* scale, float* inv_scale, float* 
 int sivo_orb_run(sivo_orb_t* h, const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypoint* kps,
                  int cap, int* n, uint8_t* desc32, uint8_t* const* pyramid_levels,
                  const size_t* pyramid_strides);
+/* Same operator with the gray image already resident in device memory (`pitch` bytes per row); the
+ * candidate / selection round trip through the host quad tree stays inside the call. */
+int sivo_orb_run_device_input(sivo_orb_t* h, const uint8_t* gray_device, int rows, int cols, size_t pitch,
+                              sivo_keypoint* kps, int cap, int* n, uint8_t* desc32);
 int sivo_orb_level_size(const sivo_orb_t* h, int rows, int cols, int level, int* level_w, int* level_h);
 /* Test hook: FAST candidates of the last run before the quad tree, per level (x, y relative to the
  * (16,16) border origin as in ComputeKeyPointsOctTree, response). */

@@ -151,6 +151,14 @@ int sivo_orb_run(sivo_orb_t* h, const uint8_t* gray, int rows, int cols, size_t 
   });
 }
 
+int sivo_orb_run_device_input(sivo_orb_t* h, const uint8_t* gray_device, int rows, int cols, size_t pitch, sivo_keypoint* kps,
+                              int cap, int* n, uint8_t* desc32) {
+  return guarded([&] {
+    if (!h) fail(SIVO_EINVAL, "null handle");
+    h->impl->run(gray_device, rows, cols, pitch, kps, cap, n, desc32, nullptr, nullptr, true);
+  });
+}
+
 int sivo_orb_level_size(const sivo_orb_t* h, int rows, int cols, int level, int* level_w, int* level_h) {
   return guarded([&] {
     if (!h) fail(SIVO_EINVAL, "null handle");

@@ -69,7 +69,7 @@ class Orb {
   Orb(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int device);
   ~Orb();
   void run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypoint* kps, int cap, int* n, uint8_t* desc,
-           uint8_t* const* pyr_out, const size_t* pyr_strides);
+           uint8_t* const* pyr_out, const size_t* pyr_strides, bool gray_on_device = false);
   void level_size(int rows, int cols, int level, int* w, int* h) const;
   const OrbTables& tables() const { return tab_; }
   int nlevels() const { return nlevels_; }

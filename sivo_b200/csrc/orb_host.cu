@@ -308,19 +308,27 @@ void Orb::ensure(int rows, int cols) {
 }
 
 void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypoint* kps, int cap, int* n, uint8_t* desc,
-              uint8_t* const* pyr_out, const size_t* pyr_strides) {
+              uint8_t* const* pyr_out, const size_t* pyr_strides, bool gray_on_device) {
   if (n) *n = 0;
   if (!gray || rows <= 0 || cols <= 0) return;  // `if (_image.empty()) return;` (:1023-1024)
   if (stride < static_cast<size_t>(cols)) fail(SIVO_EINVAL, "ORBextractor: stride smaller than a row");
   SIVO_CUDA(cudaSetDevice(device_));
   ensure(rows, cols);
   const int ncells = static_cast<int>(cells_.size());
-  uint8_t* hg = h_gray_.as<uint8_t>();
-  for (int y = 0; y < rows; ++y) memcpy(hg + static_cast<size_t>(y) * cols, gray + static_cast<size_t>(y) * stride, cols);
   cudaStream_t s = stream_;
-  SIVO_CUDA(cudaEventRecord(ev_[0], s));
-  SIVO_CUDA(cudaMemcpyAsync(d_gray_.p, hg, static_cast<size_t>(rows) * cols, cudaMemcpyHostToDevice, s));
-  orb_launch_pyramid(d_gray_.as<uint8_t>(), rows, cols, cols, d_pyr_.as<uint8_t>(), lt_, s);
+  const uint8_t* src = gray;
+  size_t src_pitch = stride;
+  if (!gray_on_device) {
+    uint8_t* hg = h_gray_.as<uint8_t>();
+    for (int y = 0; y < rows; ++y) memcpy(hg + static_cast<size_t>(y) * cols, gray + static_cast<size_t>(y) * stride, cols);
+    SIVO_CUDA(cudaEventRecord(ev_[0], s));
+    SIVO_CUDA(cudaMemcpyAsync(d_gray_.p, hg, static_cast<size_t>(rows) * cols, cudaMemcpyHostToDevice, s));
+    src = d_gray_.as<uint8_t>();
+    src_pitch = cols;
+  } else {
+    SIVO_CUDA(cudaEventRecord(ev_[0], s));
+  }
+  orb_launch_pyramid(src, rows, cols, src_pitch, d_pyr_.as<uint8_t>(), lt_, s);
   orb_launch_score(d_pyr_.as<uint8_t>(), d_score_.as<uint8_t>(), lt_, s);
   orb_launch_cells(d_score_.as<uint8_t>(), lt_, d_cells_.as<OrbCell>(), ncells, ini_th_, min_th_, d_cell_count_.as<int>(),
                    d_cell_items_.as<uint32_t>(), s);

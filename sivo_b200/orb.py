@@ -75,6 +75,16 @@ class ORBextractor:
         self.mvImagePyramid = [b[19:-19, 19:-19] for b in bufs]
         return kps[:n.value].copy(), desc[:n.value].copy()
 
+    def run_device_input(self, gray_ptr: int, rows: int, cols: int, pitch: int):
+        cap = self.nfeatures + 4 * self.nlevels + 64
+        kps = np.empty(cap, KP_DTYPE)
+        desc = np.empty((cap, 32), np.uint8)
+        n = C.c_int(0)
+        L.check(L.lib().sivo_orb_run_device_input(self._h, C.c_void_p(gray_ptr), rows, cols, C.c_size_t(pitch),
+                                                  kps.ctypes.data_as(C.c_void_p), cap, C.byref(n),
+                                                  desc.ctypes.data_as(C.c_void_p)))
+        return kps[:n.value], desc[:n.value]
+
     def candidates(self, level: int):
         n = C.c_int()
         cap = 1 << 16

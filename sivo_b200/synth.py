@@ -51,9 +51,9 @@ def stereo_frame(frame_idx: int = 0, w: int = RAW_W, h: int = RAW_H):
 
 
 def bgr_to_gray(bgr: np.ndarray) -> np.ndarray:
-    """cv::cvtColor(BGR2GRAY) for 8-bit: (B*1868 + G*9617 + R*4899 + 8192) >> 14
+    """cv::cvtColor(BGR2GRAY) for 8-bit as cv2 4.13 computes it: (B*3735 + G*19235 + R*9798 + 16384) >> 15
     (the reference converts in Tracking::GrabImageStereo, src/orbslam/Tracking.cc:187-194)."""
     b = bgr[..., 0].astype(np.int32)
     g = bgr[..., 1].astype(np.int32)
     r = bgr[..., 2].astype(np.int32)
-    return ((b * 1868 + g * 9617 + r * 4899 + 8192) >> 14).astype(np.uint8)
+    return ((b * 3735 + g * 19235 + r * 9798 + 16384) >> 15).astype(np.uint8)

@@ -1,0 +1,126 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every declared symbol,
+mirrors the reference's constructor error behaviour, and its host logic (prototxt / caffemodel readers,
+quad tree) agrees with the Python twins and the oracle.  No compute call needs a GPU here."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import make_model
+from sivo_b200 import _lib as L
+from sivo_b200 import BayesianSegNet, BayesianSegNetParams, distribute_octtree
+from sivo_b200.caffemodel import read_caffemodel, synth_weights
+from sivo_b200.prototxt import load_net, blob_shapes, param_shapes
+
+
+def test_library_exports_every_declared_symbol():
+    syms = L.declared_symbols()
+    assert len(syms) >= 25
+    lib = L.lib()
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert b"sm_100a" in lib.sivo_version()
+
+
+def test_ctor_throws_like_the_reference(model_dir):
+    # tests/test_bayesian_segnet.cpp:138-150 (std::invalid_argument on empty paths)
+    with pytest.raises(ValueError, match="model_file"):
+        BayesianSegNet(BayesianSegNetParams("", "weights.caffemodel"))
+    with pytest.raises(ValueError, match="weights_file"):
+        BayesianSegNet(BayesianSegNetParams("model.prototxt", ""))
+    # batch (= T) must be > 1 (bayesian_segnet.cpp:67-70)
+    _, _, proto, model = make_model(model_dir, "basic", T=1, H=32, W=64, width=8)
+    with pytest.raises(ValueError, match="batch size greater than 1"):
+        BayesianSegNet(BayesianSegNetParams(proto, model))
+
+
+def test_error_codes(model_dir, tmp_path):
+    _, _, proto, model = make_model(model_dir, "basic", T=2, H=32, W=64, width=8)
+    with pytest.raises(L.SivoError) as e:
+        BayesianSegNet(BayesianSegNetParams(str(tmp_path / "nope.prototxt"), model))
+    assert e.value.code == L.ENOENT
+    stub = tmp_path / "stub.caffemodel"
+    stub.write_text("version https://git-lfs.github.com/spec/v1\noid sha256:b2b0\nsize 5670476\n")
+    with pytest.raises(L.SivoError) as e:
+        BayesianSegNet(BayesianSegNetParams(proto, str(stub)))
+    assert e.value.code == L.EFORMAT and "LFS" in str(e.value)
+    bad = tmp_path / "bad.prototxt"
+    bad.write_text(open(proto).read().replace('type: "LRN"', 'type: "InnerProduct"'))
+    with pytest.raises(L.SivoError) as e:
+        BayesianSegNet(BayesianSegNetParams(str(bad), model))
+    assert e.value.code == L.EFORMAT
+
+
+def test_blank_sample_dim_is_accepted_by_the_parser():
+    text = ('name: "x"\ninput: "data"\ninput_shape {\n  dim: # SET SAMPLE SIZE HERE\n  dim: 3\n  dim: 32\n  dim: 64\n}\n'
+            'layer { name: "c" type: "Convolution" bottom: "data" top: "c" convolution_param { num_output: 15 kernel_size: 1 } }\n'
+            'layer { name: "prob" type: "Softmax" bottom: "c" top: "prob" }\n')
+    net = load_net(text)
+    assert net.input_dims == [None, 3, 32, 64]
+    assert load_net(text, T=4).T == 4
+
+
+def test_generated_prototxts_match_reference_topology():
+    ref = "/root/reference/config/bayesian_segnet"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present (GPU box)")
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs")
+
+    def sig(n):
+        return [(l.name, l.type, tuple(l.bottoms), tuple(l.tops), l.num_output, l.kernel, l.pad, l.local_size, l.alpha,
+                 l.beta, l.dropout_ratio, l.sample_weights_test, l.weight_filler) for l in n.layers]
+    for mine, theirs in (("bayesian_segnet_basic.prototxt", "basic/kitti/bayesian_segnet_basic_kitti.prototxt"),
+                         ("bayesian_segnet.prototxt", "standard/kitti/bayesian_segnet_kitti.prototxt")):
+        a = load_net(open(os.path.join(root, mine)).read())
+        b = load_net(open(os.path.join(ref, theirs)).read())
+        assert sig(a) == sig(b)
+        assert a.input_dims[1:] == b.input_dims[1:] == [3, 352, 1024]
+
+
+def test_flop_table_matches_survey():
+    # Basic 247.11 GF / sample (52.00 shared prefix), Standard 445.96 GF (134.12 shared)
+    import gen_prototxt
+    for text, total, prefix in ((gen_prototxt.basic(), 247.11, 52.00), (gen_prototxt.standard(), 445.96, 134.12)):
+        net = load_net(text)
+        shapes = blob_shapes(net)
+        tot = pre = 0.0
+        seen_drop = False
+        for ly in net.layers:
+            if ly.type == "Dropout":
+                seen_drop = True
+            if ly.type == "Convolution":
+                cin = shapes[ly.bottoms[0]][0]
+                c, h, w = shapes[ly.tops[0]]
+                f = 2.0 * cin * ly.kernel ** 2 * c * h * w / 1e9
+                tot += f
+                if not seen_drop:
+                    pre += f
+        assert abs(tot - total) < 0.01 and abs(pre - prefix) < 0.01
+
+
+def test_caffemodel_round_trip(model_dir):
+    net, w, proto, model = make_model(model_dir, "standard", T=2, H=32, W=64, widths=(8, 8, 8, 8, 8))
+    back = read_caffemodel(model)
+    assert set(back) == set(w)
+    for k in w:
+        for a, b in zip(w[k], back[k]):
+            assert a.shape == b.shape and np.array_equal(a, b)
+    assert param_shapes(net)["conv1_1"] == [(8, 3, 3, 3), (8,)]
+    assert param_shapes(net)["conv1_1_bn"] == [(1, 8, 1, 1), (1, 8, 1, 1)]
+
+
+def test_quad_tree_matches_oracle():
+    from oracle import orb_oracle as O
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        n = int(rng.integers(1, 3000))
+        w, h = int(rng.integers(100, 1000)), int(rng.integers(60, 330))
+        xs = rng.integers(0, w, n).astype(np.float32)
+        ys = rng.integers(0, h, n).astype(np.float32)
+        rs = rng.integers(7, 120, n).astype(np.float32)  # many response ties
+        tgt = int(rng.integers(1, 500))
+        a = O.distribute_octtree(xs, ys, rs, 16, 16 + w, 16, 16 + h, tgt)
+        b = distribute_octtree(xs, ys, rs, 16, 16 + w, 16, 16 + h, tgt)
+        assert list(a) == b.tolist()
+        assert len(b) <= max(tgt + 3, 1) or len(b) <= n

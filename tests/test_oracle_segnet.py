@@ -1,0 +1,158 @@
+"""Pins the SegNet oracle against the known-answer tests the reference tree holds."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import philox, segnet_oracle as S
+
+
+def caffe_pool_loop(x, k, s):
+    """Literal restatement of the CPU loop (caffe/src/caffe/layers/pooling_layer.cpp:140-187)."""
+    h, w = x.shape
+    ph, pw = int(np.ceil((h - k) / s)) + 1, int(np.ceil((w - k) / s)) + 1
+    top = np.full((ph, pw), -np.finfo(np.float32).max, np.float32)
+    mask = np.full((ph, pw), -1, np.int64)
+    for i in range(ph):
+        for j in range(pw):
+            for hh in range(i * s, min(i * s + k, h)):
+                for ww in range(j * s, min(j * s + k, w)):
+                    if x[hh, ww] > top[i, j]:
+                        top[i, j] = x[hh, ww]
+                        mask[i, j] = hh * w + ww
+    return top, mask
+
+
+def test_pool_mask_kat_3x5():
+    # caffe/src/caffe/test/test_pooling_layer.cpp:57-118 (TestForwardSquare, kernel 2 stride 1)
+    x = np.array([[1, 2, 5, 2, 3], [9, 4, 1, 4, 8], [1, 2, 5, 2, 3]], np.float32)
+    top, mask = caffe_pool_loop(x, 2, 1)
+    assert top.tolist() == [[9, 5, 5, 8], [9, 5, 5, 8]]
+    assert mask.tolist() == [[5, 2, 2, 9], [5, 12, 12, 9]]
+
+
+def test_pool_stride2_matches_caffe_loop_with_ties():
+    rng = np.random.default_rng(0)
+    x = rng.integers(0, 4, size=(2, 3, 8, 10)).astype(np.float32)  # many ties
+    v, m = S.pool_with_mask(torch.from_numpy(x))
+    for n in range(2):
+        for c in range(3):
+            t, k = caffe_pool_loop(x[n, c], 2, 2)
+            assert np.array_equal(v[n, c].numpy(), t)
+            assert np.array_equal(m[n, c].numpy(), k)
+
+
+def test_upsample_kat():
+    # caffe/src/caffe/test/test_upsample_layer.cpp:58-105: 2x2 -> 4x4, mask [2 5 / 12 14]
+    x = torch.tensor([[[[1., 2.], [3., 4.]]]])
+    m = torch.tensor([[[[2, 5], [12, 14]]]])
+    out = S.unpool(x, m)[0, 0].numpy()
+    exp = np.zeros(16, np.float32)
+    exp[[2, 5, 12, 14]] = [1, 2, 3, 4]
+    assert np.array_equal(out.reshape(-1), exp)
+
+
+def test_pool_unpool_round_trip():
+    # test_upsample_layer.cpp:193-246: values land where they came from, the rest is zero
+    rng = np.random.default_rng(1)
+    x = torch.from_numpy(rng.normal(size=(2, 3, 4, 4)).astype(np.float32))
+    v, m = S.pool_with_mask(x)
+    u = S.unpool(v, m)
+    nz = u != 0
+    assert int(nz.sum()) == 2 * 3 * 4
+    assert torch.equal(u[nz], x[nz])
+    assert int((u == 0).sum()) == (16 - 4) * 2 * 3
+
+
+def test_softmax_rows():
+    # test_softmax_layer.cpp:43-75
+    rng = np.random.default_rng(2)
+    x = torch.from_numpy(rng.normal(size=(2, 10, 2, 3)).astype(np.float32))
+    p = S.softmax_channels(x).numpy()
+    assert np.allclose(p.sum(axis=1), 1.0, atol=1e-3)
+    e = np.exp(x.numpy() - x.numpy().max(axis=1, keepdims=True))
+    assert np.allclose(p, e / e.sum(axis=1, keepdims=True), atol=1e-4)
+
+
+def test_lrn_reference_loop():
+    # ReferenceLRNForward (test_lrn_layer.cpp:55-...), tolerance 1e-5
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(2, 7, 3, 3)).astype(np.float32)
+    size, alpha, beta = 5, 1e-4, 0.75
+    ref = np.zeros_like(x)
+    for n in range(2):
+        for c in range(7):
+            lo, hi = max(0, c - 2), min(7, c + 3)
+            scale = 1.0 + (alpha / size) * (x[n, lo:hi] ** 2).sum(axis=0)
+            ref[n, c] = x[n, c] / scale ** beta
+    out = S.lrn_across(torch.from_numpy(x), size, alpha, beta, 1.0).numpy()
+    assert np.allclose(out, ref, atol=1e-5)
+
+
+def test_conv_naive_reference():
+    # caffe_conv (test_convolution_layer.cpp:22-139), tolerance 1e-4
+    import torch.nn.functional as F
+    rng = np.random.default_rng(4)
+    x = rng.normal(size=(1, 3, 6, 5)).astype(np.float32)
+    w = rng.normal(size=(4, 3, 3, 3)).astype(np.float32)
+    b = rng.normal(size=4).astype(np.float32)
+    ref = np.zeros((1, 4, 6, 5), np.float32)
+    xp = np.pad(x, ((0, 0), (0, 0), (1, 1), (1, 1)))
+    for o in range(4):
+        for y in range(6):
+            for xx in range(5):
+                ref[0, o, y, xx] = (xp[0, :, y:y + 3, xx:xx + 3] * w[o]).sum() + b[o]
+    out = F.conv2d(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b), padding=1).numpy()
+    assert np.allclose(out, ref, atol=1e-4)
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32 10 rounds
+    z = philox.philox4x32_10(0, 0, 0, 0, 0, 0)
+    assert [int(v) for v in z] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = 0xFFFFFFFF
+    z = philox.philox4x32_10(f, f, f, f, f, f)
+    assert [int(v) for v in z] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    z = philox.philox4x32_10(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0)
+    assert [int(v) for v in z] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_dropout_rule():
+    # survivors equal x * scale exactly, drop ratio within 1.96 sigma (test_neuron_layer.cpp:63-88,563-571)
+    keep = philox.dropout_keep(1234, 0, 2, 4, 64, 16, 32)
+    n = keep.size
+    frac = keep.mean()
+    assert abs(frac - 0.5) < 1.96 * np.sqrt(0.25 / n) * 2
+    assert not np.array_equal(keep[0], keep[1])  # samples draw independent masks
+    assert not np.array_equal(keep, philox.dropout_keep(1234, 1, 2, 4, 64, 16, 32))  # frames too
+    assert np.array_equal(keep, philox.dropout_keep(1234, 0, 2, 4, 64, 16, 32))
+
+
+def test_mc_reduce_semantics():
+    # bayesian_segnet.cpp:278-318: first max wins, 0 log 0 = 0, double precision
+    prob = np.zeros((2, 3, 1, 2), np.float32)
+    prob[:, :, 0, 0] = [[0.5, 0.5, 0.0], [0.5, 0.5, 0.0]]
+    prob[:, :, 0, 1] = [[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]]
+    cls, conf, ent = S.mc_reduce(prob)
+    assert cls.tolist() == [[0, 0]]
+    assert conf.tolist() == [[0.5, 0.5]]
+    assert np.allclose(ent, [[1.0, 1.0]])
+    assert ent.dtype == np.float64 and conf.dtype == np.float64 and cls.dtype == np.uint8
+
+
+def test_center_crop_rule():
+    img = np.zeros((375, 1242, 3), np.uint8)
+    img[11, 109] = 7
+    c = S.center_crop(img, 1024, 352)
+    assert c.shape == (352, 1024, 3) and c[0, 0, 0] == 7
+    assert S.center_crop(np.zeros((100, 100, 3), np.uint8), 1024, 352) is None
+
+
+def test_dedup_equals_naive(model_dir):
+    from conftest import make_model
+    net, w, _, _ = make_model(model_dir, "basic", T=3, H=32, W=64, width=8)
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, size=(32, 64, 3), dtype=np.uint8)
+    a = S.forward(net, w, img, dedup=True)
+    b = S.forward(net, w, img, dedup=False)
+    assert np.array_equal(a, b)
+    assert not np.array_equal(a[0], a[1])
