@@ -9,7 +9,7 @@
 //    SWIZZLE_128B K-major UMMA operand row.  A TMA box {64 ch, 128+K-1 px, 1 row} of the input lands one
 //    *halo row* in shared memory; out-of-image coordinates are zero-filled by TMA = the conv's zero padding.
 //  * The A operand of tap (kh, kw) for output row r is the same halo row shifted by kw pixels: the UMMA
-//    shared-memory descriptor simply starts kw*128 bytes later (base_offset carries the swizzle phase), so
+//    shared-memory descriptor simply starts kw*128 bytes later (the swizzle phase follows the absolute address), so
 //    each input row is fetched from L2 once per K rows of output instead of K*K times.
 //  * A CTA walks down a 128-px-wide column strip two output rows at a time with a ring of halo rows:
 //    every input row is loaded once per CTA (plus the K-1 overlap between vertically adjacent CTAs).
@@ -52,7 +52,7 @@ struct TcParams {
   const uint64_t* frame;
   int drop_layer;
   float drop_scale;
-  int bo_mode;             // 0: descriptor base_offset = (addr >> 7) & 7, 1: always 0 (experiment switch)
+  int bo_mode;             // 0 (default): descriptor base_offset 0; 1: (addr >> 7) & 7 (experiment switch, wrong on B200)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -103,7 +103,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int bo_mode) {
   d |= static_cast<uint64_t>(1) << 16;                        // leading byte offset (unused for swizzled K-major)
   d |= static_cast<uint64_t>(1024 >> 4) << 32;                // stride byte offset
   d |= static_cast<uint64_t>(1) << 46;                        // descriptor version (sm_100)
-  if (bo_mode == 0) d |= static_cast<uint64_t>((saddr >> 7) & 7) << 49;  // swizzle phase of the first row
+  // base_offset (bits 49-51) stays 0: measured on B200, the swizzle phase comes from the absolute shared-memory
+  // address bits [7:9], so a start address kw*128 B into a 1024-B-aligned row needs no correction
+  // (bo_mode 1 = experiment switch that sets (addr >> 7) & 7; it produces wrong results -- profiles/r1_notes.md).
+  if (bo_mode == 1) d |= static_cast<uint64_t>((saddr >> 7) & 7) << 49;
   d |= static_cast<uint64_t>(2) << 61;                        // SWIZZLE_128B
   return d;
 }
