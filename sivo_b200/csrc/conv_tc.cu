@@ -31,22 +31,24 @@ namespace sivo {
 namespace {
 
 constexpr int kTcThreads = 7 * 32;
-constexpr int kRows = 2;               // output rows per accumulator stage
 constexpr int kSlotBytes = 17 * 1024;  // one halo row: (128 + K - 1) px * 128 B, padded to a 1024-B multiple
-constexpr int kBStages = 4;
+constexpr int kMaxBStages = 6;
 
 struct TcParams {
   int H, W, N_batch;       // spatial size and batch of input == output
   int cout_total;          // channel stride of the output tensor
-  int n_tile;              // UMMA N (64 or 128)
-  int pairs_per_cta;       // row pairs one CTA walks
+  int n_tile;              // UMMA N (16 for the float logits layer, else 64 or 128)
+  int chunks;              // Cin / 64
+  int b_stages;            // weight ring depth (as many of kMaxBStages as fit in shared memory)
+  int out_f32;             // 1: 16-channel float output (logits)
+  int pairs_per_cta;       // row blocks (R output rows each) one CTA walks
   int strips;              // ceil(W / 128)
   int relu, has_bn, has_drop;
   float slope;
   const float* bias;
   const float* bn_scale;
   const float* bn_shift;
-  __half* out;
+  void* out;
   // dropout fused into the epilogue (decoder convs of Basic: decdrop4 / decdrop3)
   uint64_t seed;
   const uint64_t* frame;
@@ -136,17 +138,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int K>
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ROLL = true : one 64-channel chunk (Cin == 64); halo rows persist in the ring while the CTA walks down its
+//               strip, so each input row is fetched once per CTA.
+// ROLL = false: Cin = 64 * NC; per (row pair, chunk) the kRows+K-1 halo rows of that chunk are fetched, used by
+//               the K*K taps and released; the ring double-buffers chunks.
+template <int K, bool ROLL, int kRows>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
-  constexpr int kSlots = K + kRows - 1 + kRows;  // rows live for one pair + the next pair's new rows
+  constexpr int RK = kRows + K - 1;                  // halo rows one row pair reads (per chunk)
+  constexpr int kSlots = ROLL ? RK : 2 * RK;         // ROLL: rows are released as soon as their last tap row is issued
   constexpr int kPad = (K - 1) / 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_slots = smem;
   uint8_t* b_stages = smem + kSlots * kSlotBytes;
   const int b_bytes = p.n_tile * 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_stages + kBStages * b_bytes);
+  const int b_stride = (b_bytes + 1023) & ~1023;
+  const int kBStages = p.b_stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_stages + kMaxBStages * 0 + kBStages * b_stride);
   uint64_t* a_full = bars;                       // [kSlots]
   uint64_t* a_empty = a_full + kSlots;           // [kSlots]
   uint64_t* b_full = a_empty + kSlots;           // [kBStages]
@@ -160,12 +180,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   const int n0 = blockIdx.y * p.n_tile;
   const int img = blockIdx.z;
   const int x0 = strip * 128;
+  const int NC = ROLL ? 1 : p.chunks;
   const int total_pairs = (p.H + kRows - 1) / kRows;
   const int pair0 = rowblk * p.pairs_per_cta;
   const int npairs = min(p.pairs_per_cta, total_pairs - pair0);
   const int y_base = pair0 * kRows;              // first output row of this CTA
-  const int n_units = npairs * kRows + K - 1;    // halo rows this CTA touches: y_base - pad ... (+ n_units - 1)
-  const uint32_t tmem_cols = static_cast<uint32_t>(2 * kRows * p.n_tile);  // 256 or 512: a power of two >= 32
+  const int n_units = ROLL ? npairs * kRows + K - 1 : npairs * NC * RK;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(2 * kRows * p.n_tile)) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kSlots; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
@@ -190,9 +212,17 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       for (int u = 0; u < n_units; ++u) {
         const int slot = u % kSlots;
         const uint32_t round = static_cast<uint32_t>(u / kSlots);
+        int ch = 0, yy;
+        if (ROLL) {
+          yy = y_base - kPad + u;
+        } else {
+          const int j = u / (NC * RK), rem = u % (NC * RK);
+          ch = rem / RK;
+          yy = y_base + j * kRows - kPad + rem % RK;
+        }
         mbar_wait(a_empty + slot, (round & 1) ^ 1);
         mbar_expect_tx(a_full + slot, static_cast<uint32_t>((128 + K - 1) * 128));
-        tma_load_4d(a_slots + slot * kSlotBytes, &map_a, a_full + slot, 0, x0 - kPad, y_base - kPad + u, img);
+        tma_load_4d(a_slots + slot * kSlotBytes, &map_a, a_full + slot, ch * 64, x0 - kPad, yy, img);
       }
     }
   } else if (warp == 1) {
@@ -201,12 +231,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
       uint32_t it = 0;
       for (int j = 0; j < npairs; ++j)
-        for (int tap = 0; tap < K * K; ++tap, ++it) {
-          const int st = it % kBStages;
-          mbar_wait(b_empty + st, ((it / kBStages) & 1) ^ 1);
-          mbar_expect_tx(b_full + st, static_cast<uint32_t>(b_bytes));
-          tma_load_3d(b_stages + st * b_bytes, &map_b, b_full + st, 0, n0, tap);
-        }
+        for (int ch = 0; ch < NC; ++ch)
+          for (int tap = 0; tap < K * K; ++tap, ++it) {
+            const int st = it % kBStages;
+            mbar_wait(b_empty + st, ((it / kBStages) & 1) ^ 1);
+            mbar_expect_tx(b_full + st, static_cast<uint32_t>(b_bytes));
+            tma_load_3d(b_stages + st * b_stride, &map_b, b_full + st, ch * 64, n0, tap);
+          }
     }
   } else if (warp == 2) {
     // ===== MMA issuer =====
@@ -218,37 +249,45 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const int acc = j & 1;
         mbar_wait(t_empty + acc, ((j >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int kh = 0; kh < K; ++kh) {
-          while (waited <= j * kRows + kh + kRows - 1 && waited < n_units) {
-            mbar_wait(a_full + waited % kSlots, (waited / kSlots) & 1);
-            ++waited;
-          }
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          for (int kw = 0; kw < K; ++kw, ++it) {
-            const int st = it % kBStages;
-            mbar_wait(b_full + st, (it / kBStages) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t b_addr = smem_u32(b_stages + st * b_bytes);
-#pragma unroll
-            for (int r = 0; r < kRows; ++r) {
-              const int unit = j * kRows + r + kh;
-              const uint32_t a_addr = smem_u32(a_slots + (unit % kSlots) * kSlotBytes) + kw * 128;
-              const uint32_t d = tmem_base + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(d, umma_desc(a_addr + k * 32, p.bo_mode), umma_desc(b_addr + k * 32, p.bo_mode), idesc,
-                         (kh | kw | k) != 0);
+        for (int ch = 0; ch < NC; ++ch) {
+          const int base_u = ROLL ? j * kRows : (j * NC + ch) * RK;
+          for (int kh = 0; kh < K; ++kh) {
+            while (waited <= base_u + kh + kRows - 1 && waited < n_units) {
+              mbar_wait(a_full + waited % kSlots, (waited / kSlots) & 1);
+              ++waited;
             }
-            umma_commit(b_empty + st);  // weight stage is free once these MMAs retire
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int kw = 0; kw < K; ++kw, ++it) {
+              const int st = it % kBStages;
+              mbar_wait(b_full + st, (it / kBStages) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t b_addr = smem_u32(b_stages + st * b_stride);
+#pragma unroll
+              for (int r = 0; r < kRows; ++r) {
+                const int unit = base_u + r + kh;
+                const uint32_t a_addr = smem_u32(a_slots + (unit % kSlots) * kSlotBytes) + kw * 128;
+                const uint32_t d = tmem_base + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(d, umma_desc(a_addr + k * 32, p.bo_mode), umma_desc(b_addr + k * 32, p.bo_mode), idesc,
+                           (ch | kh | kw | k) != 0);
+              }
+              umma_commit(b_empty + st);  // weight stage is free once these MMAs retire
+            }
+            // ROLL: halo row base_u + kh (kh < kRows) is only read by tap rows <= kh of this block and by no later
+            // block, so its slot goes back to the producer now and the next block's rows stream in behind the MMAs
+            if (ROLL && kh < kRows) umma_commit(a_empty + (base_u + kh) % kSlots);
           }
+          if (ROLL && K < kRows)  // fewer tap rows than output rows: release the rest of this block's own rows
+            for (int i = K; i < kRows; ++i) umma_commit(a_empty + (base_u + i) % kSlots);
+          if (!ROLL)  // this chunk's halo rows are dead
+            for (int i = 0; i < RK; ++i) umma_commit(a_empty + (base_u + i) % kSlots);
         }
         umma_commit(t_full + acc);
-        // the first kRows halo rows of this pair are dead now
-        for (int r = 0; r < kRows; ++r) umma_commit(a_empty + (j * kRows + r) % kSlots);
       }
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> bias / BN / ReLU / dropout -> half -> global =====
+    // ===== epilogue: TMEM -> registers -> bias / BN / ReLU / dropout -> half (or float logits) -> global =====
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int x = x0 + q * 32 + lane;
     for (int j = 0; j < npairs; ++j) {
@@ -258,10 +297,29 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
         const int y = y_base + j * kRows + r;
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
+        if (p.out_f32) {  // 16-channel float logits (the convolution feeding Softmax)
+          uint32_t v[32];
+          tmem_ld16(trow, v);
+          if (y < p.H && x < p.W) {
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float t = __fadd_rn(__uint_as_float(v[i]), __ldg(p.bias + i));
+              if (p.has_bn) t = __fadd_rn(__fmul_rn(t, __ldg(p.bn_scale + i)), __ldg(p.bn_shift + i));
+              if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
+              f[i] = t;
+            }
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          }
+          continue;
+        }
         uint32_t bits[4] = {0, 0, 0, 0};
         for (int cc = 0; cc < p.n_tile; cc += 32) {
           uint32_t v[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + r) * p.n_tile + cc), v);
+          tmem_ld32(trow + cc, v);
           if (y < p.H && x < p.W) {
             const int c0 = n0 + cc;
             if (p.has_drop && ((c0 & 127) == 0 || cc == 0))
@@ -286,7 +344,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               }
               packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
             }
-            uint4* dst = reinterpret_cast<uint4*>(p.out + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout_total + c0);
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout_total + c0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
           }
@@ -336,21 +394,64 @@ struct ConvTcPlan {
   TcParams p;
   dim3 grid;
   size_t smem;
-  int k;
+  int k, rows;
+  bool roll;
 };
 
+namespace {
+// one place that names every instantiation: configure == true sets the dynamic shared-memory limit, else launches
+void conv_tc_dispatch(const ConvTcPlan& plan, cudaStream_t s, bool configure) {
+  auto go = [&](auto kern) {
+    if (configure) SIVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.smem)));
+    else kern<<<plan.grid, kTcThreads, plan.smem, s>>>(plan.map_a, plan.map_b, plan.p);
+  };
+  const int K = plan.k;
+  if (plan.roll && plan.rows == 4) { if (K == 7) go(k_conv_tc<7, true, 4>); else if (K == 3) go(k_conv_tc<3, true, 4>); else go(k_conv_tc<1, true, 4>); }
+  else if (plan.roll) { if (K == 7) go(k_conv_tc<7, true, 2>); else if (K == 3) go(k_conv_tc<3, true, 2>); else go(k_conv_tc<1, true, 2>); }
+  else { if (K == 3) go(k_conv_tc<3, false, 2>); else go(k_conv_tc<1, false, 2>); }
+}
+}  // namespace
+
+namespace {
+int tc_rows(int K, bool roll, int n_tile) { return (roll && n_tile <= 64) ? 4 : 2; }  // TMEM: 2 stages x rows x n_tile <= 512
+size_t tc_smem_bytes(int K, bool roll, int n_tile, int stages) {
+  const int rows = tc_rows(K, roll, n_tile);
+  const int rk = rows + K - 1;
+  const int slots = roll ? rk : 2 * rk;
+  const int b_stride = (n_tile * 128 + 1023) & ~1023;
+  return 1024 + static_cast<size_t>(slots) * kSlotBytes + static_cast<size_t>(stages) * b_stride + (2 * slots + 2 * stages + 4) * 8 + 16;
+}
+int tc_stages(int K, bool roll, int n_tile) {  // deepest weight ring that fits (0 = configuration does not fit)
+  for (int st = kMaxBStages; st >= 3; --st)
+    if (tc_smem_bytes(K, roll, n_tile, st) <= 227 * 1024) return st;
+  return 0;
+}
+int tc_pick_n(const Op& op, const TensorView& out, bool roll) {
+  if (out.dt == DType::F32) return 16;
+  int n = (op.cout_p % 128 == 0) ? 128 : 64;
+  if (!tc_stages(op.k, roll, n)) n = 64;
+  return n;
+}
+}  // namespace
+
 bool conv_tc_supported(const Op& op, const TensorView& in, const TensorView& out) {
-  if (in.dt != DType::F16 || out.dt != DType::F16) return false;
-  if (op.k != 3 && op.k != 7) return false;
-  if (in.cs != 64 || op.cin != 64) return false;        // one 64-channel K chunk per tap (first landing of the kernel)
-  if (op.cout % 64 || out.cs != op.cout) return false;
   if (const char* e = std::getenv("SIVO_B200_NO_TC")) if (e[0] == '1') return false;
-  return true;
+  if (in.dt != DType::F16) return false;
+  if (op.k != 1 && op.k != 3 && op.k != 7) return false;
+  if (in.cs % 64 || op.cin != in.cs) return false;
+  if (out.dt == DType::F16) {
+    if (op.cout % 64 || out.cs != op.cout) return false;
+  } else {
+    if (out.cs != 16 || op.cout > 16) return false;  // float logits, 16-channel pixels
+  }
+  const bool roll = in.cs == 64;
+  return tc_stages(op.k, roll, tc_pick_n(op, out, roll)) > 0;
 }
 
 std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, const TensorView& out, const void* w_tc) {
   auto plan = std::make_shared<ConvTcPlan>();
   const int K = op.k;
+  const bool roll = in.cs == 64;
   {  // input: NHWC half, dims (C, W, H, N)
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(in.cs), static_cast<cuuint64_t>(in.w), static_cast<cuuint64_t>(in.h),
                           static_cast<cuuint64_t>(in.n)};
@@ -359,7 +460,7 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
     cuuint32_t box[4] = {64, static_cast<cuuint32_t>(128 + K - 1), 1, 1};
     encode(&plan->map_a, in.p, 4, dims, strides, box);
   }
-  const int n_tile = (op.cout_p % 128 == 0) ? 128 : 64;
+  const int n_tile = tc_pick_n(op, out, roll);
   {  // weights: [tap][cout_p][cin_p] half, dims (cin, cout, tap)
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(op.cin_p), static_cast<cuuint64_t>(op.cout_p), static_cast<cuuint64_t>(K * K)};
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(op.cin_p) * 2, static_cast<cuuint64_t>(op.cout_p) * op.cin_p * 2};
@@ -370,37 +471,52 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   p.H = in.h; p.W = in.w; p.N_batch = in.n;
   p.cout_total = out.cs;
   p.n_tile = n_tile;
+  p.chunks = in.cs / 64;
+  p.out_f32 = out.dt == DType::F32;
   p.strips = ceil_div(in.w, 128);
-  const int total_pairs = ceil_div(in.h, kRows);
-  // enough CTAs for >= 2 waves of 148 SMs when the layer allows it, otherwise as many as there are
-  const int columns = p.strips * in.n * (op.cout_p / n_tile);
-  int want_blocks = ceil_div(2 * 148, columns);
-  int ppc = std::max(1, total_pairs / std::max(1, want_blocks));
-  ppc = std::min(ppc, 16);
+  const int rows = tc_rows(K, roll, n_tile);
+  const int total_pairs = ceil_div(in.h, rows);
+  const int cout_tiles = p.out_f32 ? 1 : op.cout_p / n_tile;
+  // row blocks per CTA: minimise (waves of 148 SMs) x (blocks per CTA + ~1 block of prologue / halo overhead)
+  const int columns = p.strips * in.n * cout_tiles;
+  int ppc = 1;
+  double best_cost = 1e30;
+  for (int c = 1; c <= std::min(total_pairs, 24); ++c) {
+    const long ctas = static_cast<long>(columns) * ceil_div(total_pairs, c);
+    const double cost = static_cast<double>((ctas + 147) / 148) * (c + (roll ? (K - 1.0) / rows * 0.5 + 0.5 : 0.3));
+    if (cost < best_cost - 1e-9) { best_cost = cost; ppc = c; }
+  }
   p.pairs_per_cta = ppc;
   p.relu = op.relu; p.has_bn = op.has_bn; p.slope = op.slope;
   p.bias = op.bias.as<float>();
   p.bn_scale = op.has_bn ? op.bn_scale.as<float>() : nullptr;
   p.bn_shift = op.has_bn ? op.bn_shift.as<float>() : nullptr;
-  p.out = static_cast<__half*>(out.p);
+  p.out = out.p;
   p.has_drop = 0; p.seed = 0; p.frame = nullptr; p.drop_layer = 0; p.drop_scale = 2.f;
   p.bo_mode = 0;
   if (const char* e = std::getenv("SIVO_B200_TC_BO")) p.bo_mode = atoi(e);
-  plan->grid = dim3(p.strips * ceil_div(total_pairs, ppc), op.cout_p / n_tile, in.n);
-  const int slots = K + kRows - 1 + kRows;
-  plan->smem = 1024 + static_cast<size_t>(slots) * kSlotBytes + static_cast<size_t>(kBStages) * n_tile * 128 + (2 * slots + 2 * kBStages + 4) * 8 + 16;
+  plan->grid = dim3(p.strips * ceil_div(total_pairs, ppc), cout_tiles, in.n);
+  p.b_stages = tc_stages(K, roll, n_tile);
+  plan->smem = tc_smem_bytes(K, roll, n_tile, p.b_stages);
   plan->k = K;
-  auto set = [&](auto kern) {
-    SIVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan->smem)));
-  };
-  if (K == 7) set(k_conv_tc<7>); else set(k_conv_tc<3>);
+  plan->roll = roll;
+  plan->rows = rows;
+  if (!roll && K == 7) fail(SIVO_EINVAL, "7x7 with Cin > 64 is not built");
+  conv_tc_dispatch(*plan, nullptr, true);
   return plan;
+}
+
+void conv_tc_set_dropout(ConvTcPlan& plan, uint64_t seed, const uint64_t* frame_dev, int layer, float scale) {
+  plan.p.has_drop = 1;
+  plan.p.seed = seed;
+  plan.p.frame = frame_dev;
+  plan.p.drop_layer = layer;
+  plan.p.drop_scale = scale;
 }
 
 void conv_tc_launch(const ConvTcPlan& plan, const Op& op, cudaStream_t s) {
   (void)op;
-  if (plan.k == 7) k_conv_tc<7><<<plan.grid, kTcThreads, plan.smem, s>>>(plan.map_a, plan.map_b, plan.p);
-  else k_conv_tc<3><<<plan.grid, kTcThreads, plan.smem, s>>>(plan.map_a, plan.map_b, plan.p);
+  conv_tc_dispatch(plan, s, false);
   SIVO_CUDA(cudaGetLastError());
 }
 

@@ -200,6 +200,13 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
         }
         if (ly.dropout_ratio != 0.5f)
           fail(SIVO_EFORMAT, "layer '%s': dropout_ratio %.3f (the keep-bit rule is specified for 0.5)", ly.name.c_str(), ly.dropout_ratio);
+        if (!ops_.empty() && ops_.back().kind == Op::Conv && ops_.back().use_tc && ops_.back().out == in && iv.n == T_ &&
+            iv.dt == DType::F16 && ly.tops[0] == ly.bottoms[0]) {
+          // in-place sampling Dropout right after a tensor-core convolution: applied in its epilogue registers
+          conv_tc_set_dropout(*ops_.back().tc, opt_.seed, d_frame_.as<uint64_t>(), drop_idx++, 1.f / (1.f - ly.dropout_ratio));
+          ops_.back().layer += "+" + ly.name;
+          break;
+        }
         Op op;
         op.kind = Op::Dropout;
         op.layer = ly.name;

@@ -82,5 +82,7 @@ class SegNet {
 bool conv_tc_supported(const Op& op, const TensorView& in, const TensorView& out);
 std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, const TensorView& out, const void* w_tc);
 void conv_tc_launch(const ConvTcPlan& plan, const Op& op, cudaStream_t s);
+// fuses the sampling Dropout that follows the convolution in place into its epilogue
+void conv_tc_set_dropout(ConvTcPlan& plan, uint64_t seed, const uint64_t* frame_dev, int layer, float scale);
 
 }  // namespace sivo

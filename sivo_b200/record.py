@@ -1,0 +1,52 @@
+"""Packed per-frame record exchanged between ranks when frames are sharded one per GPU: one
+fixed-size byte buffer per frame so a single all-gather per step moves everything the host SLAM consumes:
+header | classes u8 [H*W] | confidence f64 [H*W] | entropy f64 [H*W] | 2 x (keypoints[cap] 28 B, descriptors[cap] 32 B)."""
+from __future__ import annotations
+
+import numpy as np
+
+from .orb import KP_DTYPE
+
+HEADER = 32  # frame_id i64, n_left i64, n_right i64, reserved i64
+
+
+def record_bytes(hw: int, kp_cap: int) -> int:
+    n = HEADER + hw * 17 + 2 * kp_cap * 60
+    return (n + 255) // 256 * 256
+
+
+def offsets(hw: int, kp_cap: int):
+    o = {"classes": HEADER, "confidence": HEADER + hw, "entropy": HEADER + hw * 9}
+    base = HEADER + hw * 17
+    o["kp_left"], o["desc_left"] = base, base + kp_cap * 28
+    o["kp_right"], o["desc_right"] = base + kp_cap * 60, base + kp_cap * 60 + kp_cap * 28
+    return o
+
+
+def pack_host_part(buf: np.ndarray, hw: int, kp_cap: int, frame_id: int, kl, dl, kr, dr) -> None:
+    """Header + keypoints/descriptors (they live on the host after the quad tree); the three maps are copied
+    device-to-device into the same record by the caller."""
+    o = offsets(hw, kp_cap)
+    nl, nr = len(kl), len(kr)
+    if nl > kp_cap or nr > kp_cap:
+        raise ValueError("more keypoints than the record holds")
+    buf[:HEADER].view(np.int64)[:] = (frame_id, nl, nr, 0)
+    buf[o["kp_left"]:o["kp_left"] + nl * 28] = np.ascontiguousarray(kl, KP_DTYPE).view(np.uint8).reshape(-1)
+    buf[o["desc_left"]:o["desc_left"] + nl * 32] = np.ascontiguousarray(dl, np.uint8).reshape(-1)
+    buf[o["kp_right"]:o["kp_right"] + nr * 28] = np.ascontiguousarray(kr, KP_DTYPE).view(np.uint8).reshape(-1)
+    buf[o["desc_right"]:o["desc_right"] + nr * 32] = np.ascontiguousarray(dr, np.uint8).reshape(-1)
+
+
+def unpack(buf: np.ndarray, h: int, w: int, kp_cap: int):
+    hw = h * w
+    o = offsets(hw, kp_cap)
+    frame_id, nl, nr, _ = (int(v) for v in buf[:HEADER].view(np.int64))
+    out = {"frame_id": frame_id,
+           "classes": buf[o["classes"]:o["classes"] + hw].reshape(h, w),
+           "confidence": buf[o["confidence"]:o["confidence"] + hw * 8].view(np.float64).reshape(h, w),
+           "entropy": buf[o["entropy"]:o["entropy"] + hw * 8].view(np.float64).reshape(h, w),
+           "kp_left": buf[o["kp_left"]:o["kp_left"] + nl * 28].view(KP_DTYPE),
+           "desc_left": buf[o["desc_left"]:o["desc_left"] + nl * 32].reshape(nl, 32),
+           "kp_right": buf[o["kp_right"]:o["kp_right"] + nr * 28].view(KP_DTYPE),
+           "desc_right": buf[o["desc_right"]:o["desc_right"] + nr * 32].reshape(nr, 32)}
+    return out
