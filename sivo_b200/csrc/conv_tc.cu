@@ -54,6 +54,10 @@ struct TcParams {
   const uint64_t* frame;
   int drop_layer;
   float drop_scale;
+  // max-unpool fused into the epilogue (decoder convs): the output tensor is 2H x 2W and every pixel's channel
+  // lands in the 2x2 position its pooling mask names, zeros elsewhere (upsample_layer.cpp:74-103)
+  const uint8_t* unpool_mask;
+  int mask_n;
   int bo_mode;             // 0 (default): descriptor base_offset 0; 1: (addr >> 7) & 7 (experiment switch, wrong on B200)
 };
 
@@ -166,7 +170,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   const int b_bytes = p.n_tile * 128;
   const int b_stride = (b_bytes + 1023) & ~1023;
   const int kBStages = p.b_stages;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_stages + kMaxBStages * 0 + kBStages * b_stride);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_stages + kBStages * b_stride);
   uint64_t* a_full = bars;                       // [kSlots]
   uint64_t* a_empty = a_full + kSlots;           // [kSlots]
   uint64_t* b_full = a_empty + kSlots;           // [kBStages]
@@ -344,9 +348,30 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               }
               packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
             }
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout_total + c0);
+            if (p.unpool_mask) {
+              const uint4* mp = reinterpret_cast<const uint4*>(p.unpool_mask + ((static_cast<size_t>(img % p.mask_n) * p.H + y) * p.W + x) * p.cout_total + c0);
+              const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+              const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};  // 32 mask bytes, channel order
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+              for (int pos = 0; pos < 4; ++pos) {
+                uint32_t sel[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {  // half2 i holds channels 2i, 2i+1 -> mask bytes 2i, 2i+1
+                  const uint32_t mb = mw[i >> 1] >> ((i & 1) * 16);
+                  const uint32_t lo = ((mb & 0xFFu) == static_cast<uint32_t>(pos)) ? 0x0000FFFFu : 0u;
+                  const uint32_t hi = (((mb >> 8) & 0xFFu) == static_cast<uint32_t>(pos)) ? 0xFFFF0000u : 0u;
+                  sel[i] = packed[i] & (lo | hi);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) +
+                    ((static_cast<size_t>(img) * 2 * p.H + 2 * y + (pos >> 1)) * (2 * p.W) + 2 * x + (pos & 1)) * p.cout_total + c0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(sel[4 * i], sel[4 * i + 1], sel[4 * i + 2], sel[4 * i + 3]);
+              }
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout_total + c0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+            }
           }
         }
       }
@@ -493,6 +518,7 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   p.bn_shift = op.has_bn ? op.bn_shift.as<float>() : nullptr;
   p.out = out.p;
   p.has_drop = 0; p.seed = 0; p.frame = nullptr; p.drop_layer = 0; p.drop_scale = 2.f;
+  p.unpool_mask = nullptr; p.mask_n = 1;
   p.bo_mode = 0;
   if (const char* e = std::getenv("SIVO_B200_TC_BO")) p.bo_mode = atoi(e);
   plan->grid = dim3(p.strips * ceil_div(total_pairs, ppc), cout_tiles, in.n);
@@ -512,6 +538,12 @@ void conv_tc_set_dropout(ConvTcPlan& plan, uint64_t seed, const uint64_t* frame_
   plan.p.frame = frame_dev;
   plan.p.drop_layer = layer;
   plan.p.drop_scale = scale;
+}
+
+void conv_tc_set_unpool(ConvTcPlan& plan, const uint8_t* mask, int mask_n, void* out_2h_2w) {
+  plan.p.unpool_mask = mask;
+  plan.p.mask_n = mask_n;
+  plan.p.out = out_2h_2w;
 }
 
 void conv_tc_launch(const ConvTcPlan& plan, const Op& op, cudaStream_t s) {

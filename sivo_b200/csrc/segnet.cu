@@ -183,12 +183,21 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
         const Tensor& mt = *tensors_[m];
         if (!mt.is_mask || mt.v.c != iv.c || mt.v.h != iv.h || mt.v.w != iv.w)
           fail(SIVO_EFORMAT, "layer '%s': mask blob '%s' does not match the input", ly.name.c_str(), ly.bottoms[1].c_str());
+        const int up = add_tensor(ly.tops[0], iv.n, iv.c, iv.h * 2, iv.w * 2, iv.cs, act_);
+        if (!opt_.keep_blobs && !ops_.empty() && ops_.back().kind == Op::Conv && ops_.back().use_tc && ops_.back().out == in &&
+            iv.dt == DType::F16 && iv.cs == iv.c) {
+          // the producing tensor-core convolution scatters straight into the unpooled tensor (its own output blob
+          // is never materialised; keep_blobs keeps the two-kernel form so tests can read it)
+          conv_tc_set_unpool(*ops_.back().tc, mt.buf.as<uint8_t>(), mt.v.n, tensors_[up]->v.p);
+          ops_.back().layer += "+" + ly.name;
+          break;
+        }
         Op op;
         op.kind = Op::Unpool;
         op.layer = ly.name;
         op.in = in;
         op.in2 = m;
-        op.out = add_tensor(ly.tops[0], iv.n, iv.c, iv.h * 2, iv.w * 2, iv.cs, act_);
+        op.out = up;
         ops_.push_back(std::move(op));
         break;
       }

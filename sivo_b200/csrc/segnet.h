@@ -84,5 +84,8 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
 void conv_tc_launch(const ConvTcPlan& plan, const Op& op, cudaStream_t s);
 // fuses the sampling Dropout that follows the convolution in place into its epilogue
 void conv_tc_set_dropout(ConvTcPlan& plan, uint64_t seed, const uint64_t* frame_dev, int layer, float scale);
+// fuses the max-unpool (Upsample) that consumes the convolution's output into its epilogue; `out_2h_2w` is the
+// unpooled tensor the convolution then writes instead of its own output
+void conv_tc_set_unpool(ConvTcPlan& plan, const uint8_t* mask, int mask_n, void* out_2h_2w);
 
 }  // namespace sivo
