@@ -58,7 +58,6 @@ struct TcParams {
   // lands in the 2x2 position its pooling mask names, zeros elsewhere (upsample_layer.cpp:74-103)
   const uint8_t* unpool_mask;
   int mask_n;
-  int bo_mode;             // 0 (default): descriptor base_offset 0; 1: (addr >> 7) & 7 (experiment switch, wrong on B200)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -102,20 +101,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
-// K-major SWIZZLE_128B operand descriptor: rows of 128 B, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int bo_mode) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);        // start address
-  d |= static_cast<uint64_t>(1) << 16;                        // leading byte offset (unused for swizzled K-major)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;                // stride byte offset
-  d |= static_cast<uint64_t>(1) << 46;                        // descriptor version (sm_100)
-  // base_offset (bits 49-51) stays 0: measured on B200, the swizzle phase comes from the absolute shared-memory
-  // address bits [7:9], so a start address kw*128 B into a 1024-B-aligned row needs no correction
-  // (bo_mode 1 = experiment switch that sets (addr >> 7) & 7; it produces wrong results -- profiles/r1_notes.md).
-  if (bo_mode == 1) d |= static_cast<uint64_t>((saddr >> 7) & 7) << 49;
-  d |= static_cast<uint64_t>(2) << 61;                        // SWIZZLE_128B
-  return d;
-}
+// K-major SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): rows of 128 B, 8-row groups 1024 B apart.
+// High word: stride byte offset 1024 >> 4 (bits 32-45), version 1 (bits 46-47), base_offset 0 (bits 49-51),
+// layout SWIZZLE_128B = 2 (bits 61-63).  base_offset stays 0 even for operands that start kw*128 B into a
+// 1024-B-aligned halo row: measured on B200 (profiles/r1_notes.md) the XOR phase follows the absolute
+// shared-memory address bits [7:9]; writing (addr >> 7) & 7 there gives wrong products.
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
 
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -265,16 +256,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               const int st = it % kBStages;
               mbar_wait(b_full + st, (it / kBStages) & 1);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              const uint32_t b_addr = smem_u32(b_stages + st * b_stride);
+              // descriptors: the high word (SBO 1024 B, version 1, SWIZZLE_128B) is constant; the low word is
+              // (address >> 4) | LBO, and a K step of 16 halfs advances it by 32 B >> 4 = 2
+              const uint32_t b_lo = ((smem_u32(b_stages + st * b_stride) & 0x3FFFFu) >> 4) | (1u << 16);
+              const uint32_t first = (ch | kh | kw) ? 1u : 0u;
 #pragma unroll
               for (int r = 0; r < kRows; ++r) {
                 const int unit = base_u + r + kh;
-                const uint32_t a_addr = smem_u32(a_slots + (unit % kSlots) * kSlotBytes) + kw * 128;
+                const uint32_t a_lo = (((smem_u32(a_slots + (unit % kSlots) * kSlotBytes) + kw * 128) & 0x3FFFFu) >> 4) | (1u << 16);
                 const uint32_t d = tmem_base + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_f16(d, umma_desc(a_addr + k * 32, p.bo_mode), umma_desc(b_addr + k * 32, p.bo_mode), idesc,
-                           (ch | kh | kw | k) != 0);
+                  umma_f16(d, (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + 2 * k), (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k),
+                           idesc, first | static_cast<uint32_t>(k));
               }
               umma_commit(b_empty + st);  // weight stage is free once these MMAs retire
             }
@@ -427,7 +421,9 @@ namespace {
 // one place that names every instantiation: configure == true sets the dynamic shared-memory limit, else launches
 void conv_tc_dispatch(const ConvTcPlan& plan, cudaStream_t s, bool configure) {
   auto go = [&](auto kern) {
-    if (configure) SIVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.smem)));
+    // the limit is per kernel function, not per launch: always raise it to the full 227 KB so that plans of different
+    // sizes that share an instantiation (e.g. the 16-wide logits tile and a 64-wide layer) cannot lower it for each other
+    if (configure) SIVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     else kern<<<plan.grid, kTcThreads, plan.smem, s>>>(plan.map_a, plan.map_b, plan.p);
   };
   const int K = plan.k;
@@ -519,8 +515,6 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   p.out = out.p;
   p.has_drop = 0; p.seed = 0; p.frame = nullptr; p.drop_layer = 0; p.drop_scale = 2.f;
   p.unpool_mask = nullptr; p.mask_n = 1;
-  p.bo_mode = 0;
-  if (const char* e = std::getenv("SIVO_B200_TC_BO")) p.bo_mode = atoi(e);
   plan->grid = dim3(p.strips * ceil_div(total_pairs, ppc), cout_tiles, in.n);
   p.b_stages = tc_stages(K, roll, n_tile);
   plan->smem = tc_smem_bytes(K, roll, n_tile, p.b_stages);
