@@ -16,7 +16,7 @@
 //  * Weights [tap][cout][cin] stream through a 4-stage TMA ring, one {64 cin x N cout} tile per tap.
 //  * Accumulators live in TMEM (2 stages x R x N fp32 columns) so the epilogue of row pair j overlaps the
 //    MMAs of pair j+1.  Warp roles: 0 = halo-row TMA producer, 1 = weight TMA producer, 2 = MMA issuer
-//    (+ TMEM alloc), 3..6 = epilogue (tcgen05.ld -> bias / BN affine / ReLU / dropout -> half -> global).
+//    (+ TMEM alloc), 3 = second MMA issuer, 4..7 = epilogue (tcgen05.ld -> bias / BN affine / ReLU / dropout -> half -> global).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -30,7 +30,7 @@ namespace sivo {
 
 namespace {
 
-constexpr int kTcThreads = 7 * 32;
+constexpr int kTcThreads = 8 * 32;  // warps: 0 halo TMA, 1 weight TMA, 2-3 MMA issuers, 4-7 epilogue
 constexpr int kSlotBytes = 17 * 1024;  // one halo row: (128 + K - 1) px * 128 B, padded to a 1024-B multiple
 constexpr int kMaxBStages = 6;
 
@@ -107,6 +107,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 // 1024-B-aligned halo row: measured on B200 (profiles/r1_notes.md) the XOR phase follows the absolute
 // shared-memory address bits [7:9]; writing (addr >> 7) & 7 there gives wrong products.
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -185,9 +195,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   while (tmem_cols < static_cast<uint32_t>(2 * kRows * p.n_tile)) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kSlots; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
-    for (int i = 0; i < kBStages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
+    // two MMA issuer warps (each owns half of the output rows): every consumer-side release needs both commits
+    for (int i = 0; i < kSlots; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 2); }
+    for (int i = 0; i < kBStages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 2); mbar_init(t_empty + i, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -234,55 +245,73 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             tma_load_3d(b_stages + st * b_stride, &map_b, b_full + st, ch * 64, n0, tap);
           }
     }
-  } else if (warp == 2) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(p.n_tile >> 3) << 17) | (8u << 24);  // f16 x f16 -> f32, M = 128
-      uint32_t it = 0;
-      int waited = 0;  // halo units whose TMA has been observed
-      for (int j = 0; j < npairs; ++j) {
-        const int acc = j & 1;
-        mbar_wait(t_empty + acc, ((j >> 1) & 1) ^ 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int ch = 0; ch < NC; ++ch) {
-          const int base_u = ROLL ? j * kRows : (j * NC + ch) * RK;
-          for (int kh = 0; kh < K; ++kh) {
-            while (waited <= base_u + kh + kRows - 1 && waited < n_units) {
-              mbar_wait(a_full + waited % kSlots, (waited / kSlots) & 1);
-              ++waited;
-            }
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int kw = 0; kw < K; ++kw, ++it) {
-              const int st = it % kBStages;
-              mbar_wait(b_full + st, (it / kBStages) & 1);
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              // descriptors: the high word (SBO 1024 B, version 1, SWIZZLE_128B) is constant; the low word is
-              // (address >> 4) | LBO, and a K step of 16 halfs advances it by 32 B >> 4 = 2
-              const uint32_t b_lo = ((smem_u32(b_stages + st * b_stride) & 0x3FFFFu) >> 4) | (1u << 16);
-              const uint32_t first = (ch | kh | kw) ? 1u : 0u;
+  } else if (warp == 2 || warp == 3) {
+    // ===== MMA issuers: warp 2 owns output rows [0, kRows/2), warp 3 the rest.  The loops are warp-uniform (all 32
+    // lanes wait on the barriers) and one elected lane issues, so addresses stay in uniform registers: with N = 64 an
+    // MMA retires every 32 tensor cycles and a single issuing thread running ~14 instructions per MMA was the limiter
+    // (profiles/r1_notes.md).
+    constexpr int kMine = kRows / 2;
+    const int r_first = (warp - 2) * kMine;
+    const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(p.n_tile >> 3) << 17) | (8u << 24);  // f16 x f16 -> f32, M = 128
+    const uint32_t a_base = smem_u32(a_slots), b_base = smem_u32(b_stages);
+    int st = 0;
+    uint32_t b_phase = 0;
+    int waited = 0;  // halo units whose TMA has been observed
+    for (int j = 0; j < npairs; ++j) {
+      const int acc = j & 1;
+      mbar_wait(t_empty + acc, ((j >> 1) & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int ch = 0; ch < NC; ++ch) {
+        const int base_u = ROLL ? j * kRows : (j * NC + ch) * RK;
+        for (int kh = 0; kh < K; ++kh) {
+          while (waited <= base_u + kh + kRows - 1 && waited < n_units) {
+            mbar_wait(a_full + waited % kSlots, (waited / kSlots) & 1);
+            ++waited;
+          }
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint32_t a_row_lo[kMine], d_row[kMine];
 #pragma unroll
-              for (int r = 0; r < kRows; ++r) {
-                const int unit = base_u + r + kh;
-                const uint32_t a_lo = (((smem_u32(a_slots + (unit % kSlots) * kSlotBytes) + kw * 128) & 0x3FFFFu) >> 4) | (1u << 16);
-                const uint32_t d = tmem_base + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
+          for (int m = 0; m < kMine; ++m) {
+            const int unit = base_u + r_first + m + kh;
+            a_row_lo[m] = (((a_base + (unit % kSlots) * kSlotBytes) & 0x3FFFFu) >> 4) | (1u << 16);
+            d_row[m] = tmem_base + static_cast<uint32_t>((acc * kRows + r_first + m) * p.n_tile);
+          }
+          const uint32_t first_row = (ch | kh) ? 1u : 0u;
+#pragma unroll
+          for (int kw = 0; kw < K; ++kw) {
+            mbar_wait(b_full + st, b_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // descriptors: the high word is constant; the low word is (address >> 4) | LBO; a K step of 16 halfs
+            // advances it by 32 B >> 4 = 2, a tap column by 128 B >> 4 = 8
+            const uint32_t b_lo = (((b_base + st * b_stride) & 0x3FFFFu) >> 4) | (1u << 16);
+            if (elect_one()) {
+#pragma unroll
+              for (int m = 0; m < kMine; ++m) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_f16(d, (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + 2 * k), (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k),
-                           idesc, first | static_cast<uint32_t>(k));
+                  umma_f16(d_row[m], (static_cast<uint64_t>(kDescHi) << 32) | (a_row_lo[m] + 8 * kw + 2 * k),
+                           (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k), idesc, first_row | static_cast<uint32_t>(kw | k));
               }
-              umma_commit(b_empty + st);  // weight stage is free once these MMAs retire
+              umma_commit(b_empty + st);  // weight stage is free once both issuers' MMAs retire
             }
-            // ROLL: halo row base_u + kh (kh < kRows) is only read by tap rows <= kh of this block and by no later
-            // block, so its slot goes back to the producer now and the next block's rows stream in behind the MMAs
-            if (ROLL && kh < kRows) umma_commit(a_empty + (base_u + kh) % kSlots);
+            __syncwarp();
+            if (++st == kBStages) { st = 0; b_phase ^= 1; }
           }
+          // ROLL: halo row base_u + kh (kh < kRows) is only read by tap rows <= kh of this block and by no later
+          // block, so its slot goes back to the producer now and the next block's rows stream in behind the MMAs
+          if (ROLL && kh < kRows && elect_one()) umma_commit(a_empty + (base_u + kh) % kSlots);
+          __syncwarp();
+        }
+        if (elect_one()) {
           if (ROLL && K < kRows)  // fewer tap rows than output rows: release the rest of this block's own rows
             for (int i = K; i < kRows; ++i) umma_commit(a_empty + (base_u + i) % kSlots);
           if (!ROLL)  // this chunk's halo rows are dead
             for (int i = 0; i < RK; ++i) umma_commit(a_empty + (base_u + i) % kSlots);
         }
-        umma_commit(t_full + acc);
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(t_full + acc);
+      __syncwarp();
     }
   } else {
     // ===== epilogue: TMEM -> registers -> bias / BN / ReLU / dropout -> half (or float logits) -> global =====

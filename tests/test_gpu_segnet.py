@@ -46,10 +46,11 @@ def check_masks_are_ties(net, blobs, masks, prec):
         v_dev = torch.gather(flat, 2, m.reshape(m.shape[0], m.shape[1], -1))
         v_own = torch.gather(flat, 2, own.reshape(own.shape[0], own.shape[1], -1))
         diff = (m != own).reshape(m.shape[0], m.shape[1], -1)
-        # 2 ulp of the stored precision, plus the fp32 summation noise of the producing convolution (relative to
-        # the blob's scale, not to the value: small outputs come from cancellation of O(scale) terms)
+        # 2 ulp of the stored precision, plus the input-rounding noise of the producing convolution: each output sums
+        # hundreds of stored inputs, ~0.2 % of which sit one ulp apart between two fp32 summation orders, so outputs
+        # carry absolute noise of order 1e-4..1e-3 of the blob's scale whatever their own magnitude (fp32 engine: 1e-6)
         rel = 2.0 ** -9 if prec == "fp16" else 2.0 ** -20
-        ok = (v_own - v_dev).abs() <= rel * v_own.abs() + 2e-5 * float(x.abs().max())
+        ok = (v_own - v_dev).abs() <= rel * v_own.abs() + (1e-3 if prec == "fp16" else 2e-6) * float(x.abs().max())
         assert bool(ok[diff].all()), (ly.name, float((v_own - v_dev).abs()[diff].max()), float(x.abs().max()))
         flips += int(diff.sum())
         total += diff.numel()
