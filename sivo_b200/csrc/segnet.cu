@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace sivo {
@@ -30,29 +31,40 @@ int SegNet::add_tensor(const std::string& name, int n, int c, int h, int w, int 
 }
 
 void SegNet::prepare_conv(Op& op, const std::vector<Blob>& cb, const std::vector<Blob>* bn) {
-  const int K = op.k, cin = op.cin, cout = op.cout;
+  // K is the layer's kernel size; a tap-expanded layer (expand_k > 0) stores it as one tap over expand_k*blk channels
+  const int K = op.expand_k ? op.expand_k : op.k, cin = op.expand_k ? 3 : op.cin, cout = op.cout;
+  const int taps = op.expand_k ? 1 : K * K;
+  auto slot = [&](int t, int ci, int& tap, int& cidx) {
+    if (op.expand_k) { tap = 0; cidx = (t / K) * op.expand_blk + (t % K) * 4 + ci; }
+    else { tap = t; cidx = ci; }
+  };
   if (cb.empty() || cb[0].shape.size() != 4 || cb[0].shape[0] != cout || cb[0].shape[1] != cin || cb[0].shape[2] != K ||
       cb[0].shape[3] != K)
     fail(SIVO_EFORMAT, "layer '%s': weight blob shape does not match (%d,%d,%d,%d) (net.cpp:750-785 would CHECK-fail)",
          op.layer.c_str(), cout, cin, K, K);
   const bool half = act_ == DType::F16;
   const float* W = cb[0].data.data();
-  std::vector<float> ws(static_cast<size_t>(K) * K * op.cin_p * op.cout_p, 0.f);
+  std::vector<float> ws(static_cast<size_t>(taps) * op.cin_p * op.cout_p, 0.f);
   for (int co = 0; co < cout; ++co)
     for (int ci = 0; ci < cin; ++ci)
       for (int t = 0; t < K * K; ++t) {
         float v = W[(static_cast<size_t>(co) * cin + ci) * K * K + t];
-        ws[(static_cast<size_t>(t) * op.cin_p + ci) * op.cout_p + co] = half ? through_half(v) : v;
+        int tap, cidx;
+        slot(t, ci, tap, cidx);
+        ws[(static_cast<size_t>(tap) * op.cin_p + cidx) * op.cout_p + co] = half ? through_half(v) : v;
       }
   op.w_simt.alloc(ws.size() * sizeof(float));
   SIVO_CUDA(cudaMemcpy(op.w_simt.p, ws.data(), ws.size() * sizeof(float), cudaMemcpyHostToDevice));
   if (half) {  // tensor-core layout: [tap][cout_p][cin_p] half, K(=cin)-major rows
-    std::vector<__half> wt(static_cast<size_t>(K) * K * op.cout_p * op.cin_p, __float2half_rn(0.f));
+    std::vector<__half> wt(static_cast<size_t>(taps) * op.cout_p * op.cin_p, __float2half_rn(0.f));
     for (int co = 0; co < cout; ++co)
       for (int ci = 0; ci < cin; ++ci)
-        for (int t = 0; t < K * K; ++t)
-          wt[(static_cast<size_t>(t) * op.cout_p + co) * op.cin_p + ci] =
+        for (int t = 0; t < K * K; ++t) {
+          int tap, cidx;
+          slot(t, ci, tap, cidx);
+          wt[(static_cast<size_t>(tap) * op.cout_p + co) * op.cin_p + cidx] =
               __float2half_rn(W[(static_cast<size_t>(co) * cin + ci) * K * K + t]);
+        }
     op.w_tc.alloc(wt.size() * sizeof(__half));
     SIVO_CUDA(cudaMemcpy(op.w_tc.p, wt.data(), wt.size() * sizeof(__half), cudaMemcpyHostToDevice));
   }
@@ -123,6 +135,24 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
         op.in = in;
         op.k = ly.kernel; op.pad = ly.pad; op.cin = iv.c; op.cout = ly.num_output;
         op.cin_p = iv.cs;
+        const char* no_tc = std::getenv("SIVO_B200_NO_TC");
+        if (iv.cs == 4 && iv.c == 3 && act_ == DType::F16 && opt_.engine != SIVO_ENGINE_SIMT && (ly.kernel == 7 || ly.kernel == 3) &&
+            ly.num_output % 64 == 0 && !(no_tc && no_tc[0] == '1')) {
+          // 3-channel first layer: expand the KxK taps into channels once, then it is a 1x1 tensor-core convolution
+          const int blk = (ly.kernel * 4 + 15) / 16 * 16, cs_e = round_up(ly.kernel * blk, 64);
+          Op ex;
+          ex.kind = Op::Expand;
+          ex.layer = ly.name + "/expand";
+          ex.in = in;
+          ex.k = ly.kernel;
+          ex.expand_blk = blk;
+          ex.out = add_tensor("__expand_" + ly.name, iv.n, cs_e, iv.h, iv.w, cs_e, act_);
+          ops_.push_back(std::move(ex));
+          op.in = ops_.back().out;
+          op.expand_k = ly.kernel; op.expand_blk = blk;
+          op.k = 1; op.pad = 0; op.cin = cs_e; op.cin_p = cs_e;
+        }
+        const TensorView civ = tensors_[op.in]->v;  // the tensor the convolution actually reads
         op.cout_p = round_up(op.cout, 64);
         const std::vector<Blob>* bn = nullptr;
         size_t lj = li + 1;
@@ -148,12 +178,12 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
         auto it = weights.find(ly.name);
         if (it == weights.end()) fail(SIVO_EFORMAT, "caffemodel has no blobs for layer '%s'", ly.name.c_str());
         prepare_conv(op, it->second, bn);
-        op.flops = 2.0 * op.cin * op.k * op.k * op.cout * iv.h * iv.w * iv.n;
+        op.flops = 2.0 * iv.c * ly.kernel * ly.kernel * op.cout * iv.h * iv.w * iv.n;  // algorithmic, whatever the mapping
         flops_dedup += op.flops;
         flops_naive += op.flops / iv.n * T_;
         if (opt_.engine != SIVO_ENGINE_SIMT && act_ == DType::F16 &&
-            conv_tc_supported(op, iv, tensors_[op.out]->v)) {
-          op.tc = conv_tc_plan(op, iv, tensors_[op.out]->v, op.w_tc.p);
+            conv_tc_supported(op, civ, tensors_[op.out]->v)) {
+          op.tc = conv_tc_plan(op, civ, tensors_[op.out]->v, op.w_tc.p);
           op.use_tc = true;
         } else if (opt_.engine == SIVO_ENGINE_TCGEN05 && op.cin_p % 64 == 0 && !logits) {
           fail(SIVO_EINVAL, "layer '%s': tcgen05 engine requested but the shape is not supported", ly.name.c_str());
@@ -301,6 +331,9 @@ void SegNet::run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* co
     switch (op.kind) {
       case Op::Input:
         launch_input_u8(bgr_dev, tensors_[op.out]->v, s);
+        break;
+      case Op::Expand:
+        launch_expand_taps(tensors_[op.in]->v, tensors_[op.out]->v, op.k, op.expand_blk, s);
         break;
       case Op::LRN:
         launch_lrn(tensors_[op.in]->v, tensors_[op.out]->v, op.lrn_size, op.lrn_alpha, op.lrn_beta, op.lrn_k, s);

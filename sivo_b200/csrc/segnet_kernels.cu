@@ -287,6 +287,33 @@ __global__ void k_mc_reduce_generic(const float* __restrict__ logits, int T, int
   if (entropy) entropy[i] = ent;
 }
 
+// ---- tap expansion for the 3-channel first convolution: out[y][x][kh*blk + kw*4 + c] = in[y+kh-pad][x+kw-pad][c]
+// (zero outside the image = the convolution's zero padding), so that conv1 becomes a 1x1 convolution over
+// K*blk channels that the tensor-core kernel can run (K*K*3 = 147 of 256 K-slots useful for the 7x7 layer).
+template <typename AT>
+__global__ void k_expand_taps(const AT* __restrict__ in, AT* __restrict__ out, int N, int H, int W, int K, int blk, int cs_out) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // one thread per (n, y, x, kh-or-pad-block)
+  const int groups = cs_out / blk;
+  size_t total = static_cast<size_t>(N) * H * W * groups;
+  if (i >= total) return;
+  const int g = i % groups;
+  size_t r = i / groups;
+  const int x = r % W;
+  r /= W;
+  const int y = r % H;
+  const int n = r / H;
+  AT* d = out + ((static_cast<size_t>(n) * H + y) * W + x) * cs_out + g * blk;
+  const int pad = (K - 1) / 2;
+  const int yy = y + g - pad;
+  for (int j = 0; j < blk; ++j) {
+    const int kw = j >> 2, c = j & 3;
+    const int xx = x + kw - pad;
+    float v = 0.f;
+    if (g < K && kw < K && yy >= 0 && yy < H && xx >= 0 && xx < W) v = ld_act(in + ((static_cast<size_t>(n) * H + yy) * W + xx) * 4 + c);
+    st_act(d + j, v);
+  }
+}
+
 // ---- layout converters for the test hooks
 template <typename AT>
 __global__ void k_nchw_to_act(const float* __restrict__ src, AT* __restrict__ dst, int N, int C, int HW, int cs) {
@@ -390,6 +417,13 @@ void launch_conv_simt(const ConvParams& p, cudaStream_t s) {
   } else {
     conv_dispatch<float, float>(p, s);
   }
+}
+
+void launch_expand_taps(TensorView in, TensorView out, int K, int blk, cudaStream_t s) {
+  size_t total = static_cast<size_t>(out.n) * out.h * out.w * (out.cs / blk);
+  DISPATCH_AT(in.dt, (k_expand_taps<AT><<<blocks_for(total, 256), 256, 0, s>>>(static_cast<const AT*>(in.p), static_cast<AT*>(out.p),
+                                                                               out.n, out.h, out.w, K, blk, out.cs)));
+  SIVO_CUDA(cudaGetLastError());
 }
 
 void launch_pool(TensorView in, TensorView out, uint8_t* mask, cudaStream_t s) {

@@ -39,6 +39,8 @@ struct DropoutParams {
 void launch_input_u8(const uint8_t* bgr_hwc, TensorView out, cudaStream_t s);
 void launch_lrn(TensorView in, TensorView out, int size, float alpha, float beta, float k, cudaStream_t s);
 void launch_conv_simt(const ConvParams& p, cudaStream_t s);
+// 4-channel input -> K*blk-channel tap-expanded tensor (see k_expand_taps)
+void launch_expand_taps(TensorView in, TensorView out, int K, int blk, cudaStream_t s);
 void launch_pool(TensorView in, TensorView out, uint8_t* mask, cudaStream_t s);
 // mask_n: batch of the mask tensor (1 when the pool ran in the sample-invariant prefix)
 void launch_unpool(TensorView in, const uint8_t* mask, int mask_n, TensorView out, cudaStream_t s);
