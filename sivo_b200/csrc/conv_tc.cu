@@ -58,6 +58,12 @@ struct TcParams {
   // lands in the 2x2 position its pooling mask names, zeros elsewhere (upsample_layer.cpp:74-103)
   const uint8_t* unpool_mask;
   int mask_n;
+  // 1x1 classifier fused into the epilogue (the layer feeding Softmax): logits[j] = cls_b[j] + sum_c half(out[c]) * cls_w[c][j];
+  // the 64-channel output itself is then never written
+  const float* cls_w;      // [64][cls_stride] float (half-rounded values), j < 16 used
+  const float* cls_b;      // [16]
+  float* cls_out;          // [N][H][W][16]
+  int cls_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -179,6 +185,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint64_t* t_full = b_empty + kBStages;         // [2]
   uint64_t* t_empty = t_full + 2;                // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  float* s_cls = reinterpret_cast<float*>(tmem_slot + 4);  // [64][16] classifier weights (only when p.cls_w)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int strip = blockIdx.x % p.strips, rowblk = blockIdx.x / p.strips;
@@ -202,6 +209,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  if (p.cls_w)
+    for (int e = threadIdx.x; e < 64 * 16; e += kTcThreads) s_cls[e] = p.cls_w[(e >> 4) * p.cls_stride + (e & 15)];
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -343,6 +352,37 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           }
           continue;
         }
+        if (p.cls_w) {  // conv (+bias) -> half rounding (as the unfused path stores it) -> 1x1 classifier -> float logits
+          float l[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) l[jj] = __ldg(p.cls_b + jj);
+          for (int cc = 0; cc < 64; cc += 32) {
+            uint32_t v[32];
+            tmem_ld32(trow + cc, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float t = __fadd_rn(__uint_as_float(v[i]), __ldg(p.bias + cc + i));
+              if (p.has_bn) t = __fadd_rn(__fmul_rn(t, __ldg(p.bn_scale + cc + i)), __ldg(p.bn_shift + cc + i));
+              if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
+              const float hv = __half2float(__float2half_rn(t));
+              const float4* w4 = reinterpret_cast<const float4*>(s_cls + (cc + i) * 16);
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 w = w4[q4];
+                l[4 * q4] = fmaf(hv, w.x, l[4 * q4]);
+                l[4 * q4 + 1] = fmaf(hv, w.y, l[4 * q4 + 1]);
+                l[4 * q4 + 2] = fmaf(hv, w.z, l[4 * q4 + 2]);
+                l[4 * q4 + 3] = fmaf(hv, w.w, l[4 * q4 + 3]);
+              }
+            }
+          }
+          if (y < p.H && x < p.W) {
+            float4* dst = reinterpret_cast<float4*>(p.cls_out + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_float4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
+          }
+          continue;
+        }
         uint32_t bits[4] = {0, 0, 0, 0};
         for (int cc = 0; cc < p.n_tile; cc += 32) {
           uint32_t v[32];
@@ -469,7 +509,7 @@ size_t tc_smem_bytes(int K, bool roll, int n_tile, int stages) {
   const int rk = rows + K - 1;
   const int slots = roll ? rk : 2 * rk;
   const int b_stride = (n_tile * 128 + 1023) & ~1023;
-  return 1024 + static_cast<size_t>(slots) * kSlotBytes + static_cast<size_t>(stages) * b_stride + (2 * slots + 2 * stages + 4) * 8 + 16;
+  return 1024 + static_cast<size_t>(slots) * kSlotBytes + static_cast<size_t>(stages) * b_stride + (2 * slots + 2 * stages + 4) * 8 + 16 + 64 * 16 * 4;  // barriers, TMEM slot, fused-classifier weights
 }
 int tc_stages(int K, bool roll, int n_tile) {  // deepest weight ring that fits (0 = configuration does not fit)
   for (int st = kMaxBStages; st >= 3; --st)
@@ -544,6 +584,7 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   p.out = out.p;
   p.has_drop = 0; p.seed = 0; p.frame = nullptr; p.drop_layer = 0; p.drop_scale = 2.f;
   p.unpool_mask = nullptr; p.mask_n = 1;
+  p.cls_w = nullptr; p.cls_b = nullptr; p.cls_out = nullptr; p.cls_stride = 0;
   plan->grid = dim3(p.strips * ceil_div(total_pairs, ppc), cout_tiles, in.n);
   p.b_stages = tc_stages(K, roll, n_tile);
   plan->smem = tc_smem_bytes(K, roll, n_tile, p.b_stages);
@@ -567,6 +608,17 @@ void conv_tc_set_unpool(ConvTcPlan& plan, const uint8_t* mask, int mask_n, void*
   plan.p.unpool_mask = mask;
   plan.p.mask_n = mask_n;
   plan.p.out = out_2h_2w;
+}
+
+bool conv_tc_can_fuse_classifier(const ConvTcPlan& plan) {
+  return plan.roll && plan.p.n_tile == 64 && plan.p.cout_total == 64 && !plan.p.out_f32 && !plan.p.unpool_mask && !plan.p.has_drop;
+}
+
+void conv_tc_set_classifier(ConvTcPlan& plan, const float* w_cin_by_cout, int stride, const float* bias, float* logits) {
+  plan.p.cls_w = w_cin_by_cout;
+  plan.p.cls_stride = stride;
+  plan.p.cls_b = bias;
+  plan.p.cls_out = logits;
 }
 
 void conv_tc_launch(const ConvTcPlan& plan, const Op& op, cudaStream_t s) {

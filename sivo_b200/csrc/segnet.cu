@@ -181,6 +181,17 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
         op.flops = 2.0 * iv.c * ly.kernel * ly.kernel * op.cout * iv.h * iv.w * iv.n;  // algorithmic, whatever the mapping
         flops_dedup += op.flops;
         flops_naive += op.flops / iv.n * T_;
+        if (logits && !opt_.keep_blobs && op.k == 1 && op.cin == 64 && op.cout <= 16 && !op.relu && !bn && !ops_.empty() &&
+            ops_.back().kind == Op::Conv && ops_.back().use_tc && ops_.back().out == in && conv_tc_can_fuse_classifier(*ops_.back().tc)) {
+          // 1x1 classifier straight after a tensor-core convolution: computed in that convolution's epilogue from the
+          // half-rounded activations, so the 64-channel tensor is never written or re-read
+          conv_tc_set_classifier(*ops_.back().tc, op.w_simt.as<float>(), op.cout_p, op.bias.as<float>(),
+                                 static_cast<float*>(tensors_[op.out]->v.p));
+          ops_.back().layer += "+" + ly.name;
+          fused_.push_back(std::move(op));
+          li = lj - 1;
+          break;
+        }
         if (opt_.engine != SIVO_ENGINE_SIMT && act_ == DType::F16 &&
             conv_tc_supported(op, civ, tensors_[op.out]->v)) {
           op.tc = conv_tc_plan(op, civ, tensors_[op.out]->v, op.w_tc.p);

@@ -73,6 +73,7 @@ class SegNet {
   std::vector<std::unique_ptr<Tensor>> tensors_;
   std::map<std::string, int> by_name_;
   std::vector<Op> ops_;
+  std::vector<Op> fused_;  // ops folded into a neighbour's epilogue; kept alive for their weight buffers
   cudaStream_t stream_ = nullptr;
   DevBuf d_bgr_, d_classes_, d_conf_, d_ent_, d_frame_;
   PinnedBuf h_in_, h_classes_, h_conf_, h_ent_, h_frame_;
@@ -88,5 +89,8 @@ void conv_tc_set_dropout(ConvTcPlan& plan, uint64_t seed, const uint64_t* frame_
 // fuses the max-unpool (Upsample) that consumes the convolution's output into its epilogue; `out_2h_2w` is the
 // unpooled tensor the convolution then writes instead of its own output
 void conv_tc_set_unpool(ConvTcPlan& plan, const uint8_t* mask, int mask_n, void* out_2h_2w);
+// fuses a following 1x1 convolution to <= 16 float logits (the layer feeding Softmax) into the epilogue
+bool conv_tc_can_fuse_classifier(const ConvTcPlan& plan);
+void conv_tc_set_classifier(ConvTcPlan& plan, const float* w_cin_by_cout, int stride, const float* bias, float* logits);
 
 }  // namespace sivo

@@ -238,10 +238,21 @@ __global__ void k_mc_reduce(const float* __restrict__ logits, int T, int cs, int
   for (int c = 0; c < C; ++c) acc[c] = 0.0;
   for (int t = 0; t < T; ++t) {
     const float* s = logits + (static_cast<size_t>(t) * hw + i) * cs;
-    float x[C];
+    float x[16];
+    if (cs == 16) {  // one 64-byte pixel: four 128-bit loads instead of 15 strided scalar ones
+      const float4* s4 = reinterpret_cast<const float4*>(s);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = __ldg(s4 + q);
+        x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) x[c] = s[c];
+    }
     float m = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < C; ++c) { x[c] = s[c]; m = fmaxf(m, x[c]); }
+    for (int c = 0; c < C; ++c) m = fmaxf(m, x[c]);
     float sum = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) { x[c] = expf(__fsub_rn(x[c], m)); sum = __fadd_rn(sum, x[c]); }
@@ -305,11 +316,24 @@ __global__ void k_expand_taps(const AT* __restrict__ in, AT* __restrict__ out, i
   AT* d = out + ((static_cast<size_t>(n) * H + y) * W + x) * cs_out + g * blk;
   const int pad = (K - 1) / 2;
   const int yy = y + g - pad;
+  const bool row_ok = g < K && yy >= 0 && yy < H;
+  if (sizeof(AT) == 2) {  // half: one 4-channel pixel = 8 bytes; write the block as 16-byte vectors
+    const uint2* src = reinterpret_cast<const uint2*>(in) + (static_cast<size_t>(n) * H + yy) * W;
+    uint4* dst = reinterpret_cast<uint4*>(d);
+    for (int q = 0; q < blk / 8; ++q) {
+      uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
+      const int xa = x + 2 * q - pad, xb = xa + 1;
+      if (row_ok && 2 * q < K && xa >= 0 && xa < W) a = __ldg(src + xa);
+      if (row_ok && 2 * q + 1 < K && xb >= 0 && xb < W) b = __ldg(src + xb);
+      dst[q] = make_uint4(a.x, a.y, b.x, b.y);
+    }
+    return;
+  }
   for (int j = 0; j < blk; ++j) {
     const int kw = j >> 2, c = j & 3;
     const int xx = x + kw - pad;
     float v = 0.f;
-    if (g < K && kw < K && yy >= 0 && yy < H && xx >= 0 && xx < W) v = ld_act(in + ((static_cast<size_t>(n) * H + yy) * W + xx) * 4 + c);
+    if (row_ok && kw < K && xx >= 0 && xx < W) v = ld_act(in + ((static_cast<size_t>(n) * H + yy) * W + xx) * 4 + c);
     st_act(d + j, v);
   }
 }

@@ -193,8 +193,9 @@ def test_tcgen05_conv_equals_simt_conv_on_device(model_dir):
 
 
 def test_fused_epilogues_equal_the_unfused_ops(model_dir):
-    """keep_blobs keeps max-unpool as its own kernel; the default build scatters from the tensor-core convolution's
-    epilogue.  Same arithmetic, so the operator's outputs must be identical bit for bit."""
+    """keep_blobs keeps max-unpool and the 1x1 classifier as their own kernels; the default build scatters from the
+    tensor-core convolution's epilogue and computes the logits there.  Unpool is the same arithmetic; the fused
+    classifier sums its 64 products in a different fp32 order, so logits agree to ~1e-6 relative."""
     net, w, proto, model = _full_model(model_dir)
     left, _ = stereo_frame(2)
     res = []
@@ -202,5 +203,7 @@ def test_fused_epilogues_equal_the_unfused_ops(model_dir):
         seg = BayesianSegNet(BayesianSegNetParams(proto, model), seed=1234, T=2, precision="fp16", engine="auto", keep_blobs=keep)
         seg.set_frame(5)
         res.append(seg.segmentImage(left))
-    for a, b in zip(*res):
-        assert np.array_equal(a, b)
+    (c0, f0, e0), (c1, f1, e1) = res
+    assert (c0 != c1).mean() < 1e-4
+    assert np.abs(e0 - e1).max() < 1e-2 and np.median(np.abs(e0 - e1)) < 1e-9
+    assert np.abs(f0 - f1).max() < 1e-2
