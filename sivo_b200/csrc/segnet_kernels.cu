@@ -272,6 +272,58 @@ __global__ void k_mc_reduce(const float* __restrict__ logits, int T, int cs, int
   if (entropy) entropy[i] = ent;
 }
 
+// Same reduction with four lanes per pixel (one float4 = 4 classes each): a warp reads 512 contiguous bytes per
+// sample and there are 4x more threads in flight, which is what this HBM-bound pass needs.  The softmax max / sum and
+// the final argmax / entropy are combined with xor-shuffles inside the 4-lane group (first maximum still wins).
+__global__ void k_mc_reduce_quad(const float* __restrict__ logits, int T, int C, int hw, uint8_t* __restrict__ classes,
+                                 double* __restrict__ conf, double* __restrict__ entropy) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pix = gid >> 2, q = gid & 3;
+  const bool live = pix < hw;
+  const int pp = live ? pix : hw - 1;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int t = 0; t < T; ++t) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(logits + (static_cast<size_t>(t) * hw + pp) * 16) + q);
+    float x[4] = {v.x, v.y, v.z, v.w};
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (q * 4 + j < C) m = fmaxf(m, x[j]);
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      x[j] = (q * 4 + j < C) ? expf(__fsub_rn(x[j], m)) : 0.f;
+      sum = __fadd_rn(sum, x[j]);
+    }
+    sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 1));
+    sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 2));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] += static_cast<double>(__fdiv_rn(x[j], sum));
+  }
+  double best = -1.0, ent = 0.0;
+  int arg = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (q * 4 + j >= C) continue;
+    const double pm = acc[j] / static_cast<double>(T);
+    if (pm > best) { best = pm; arg = q * 4 + j; }
+    if (pm != 0.0) ent += -1.0 * pm * log2(pm);
+  }
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    ent += __shfl_xor_sync(0xffffffffu, ent, o);
+    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  if (live && q == 0) {
+    if (classes) classes[pix] = static_cast<uint8_t>(arg);
+    if (conf) conf[pix] = best;
+    if (entropy) entropy[pix] = ent;
+  }
+}
+
 __global__ void k_mc_reduce_generic(const float* __restrict__ logits, int T, int C, int cs, int hw,
                                     uint8_t* __restrict__ classes, double* __restrict__ conf,
                                     double* __restrict__ entropy) {
@@ -475,7 +527,8 @@ void launch_dropout(TensorView in, TensorView out, const DropoutParams& d, float
 
 void launch_mc_reduce(const float* logits, int T, int C, int cs, int hw, uint8_t* classes, double* conf, double* entropy,
                       cudaStream_t s) {
-  if (C == 15) k_mc_reduce<15><<<blocks_for(hw, 128), 128, 0, s>>>(logits, T, cs, hw, classes, conf, entropy);
+  if (cs == 16 && C <= 16) k_mc_reduce_quad<<<blocks_for(static_cast<size_t>(hw) * 4, 256), 256, 0, s>>>(logits, T, C, hw, classes, conf, entropy);
+  else if (C == 15) k_mc_reduce<15><<<blocks_for(hw, 128), 128, 0, s>>>(logits, T, cs, hw, classes, conf, entropy);
   else k_mc_reduce_generic<<<blocks_for(hw, 128), 128, 0, s>>>(logits, T, C, cs, hw, classes, conf, entropy);
   SIVO_CUDA(cudaGetLastError());
 }
