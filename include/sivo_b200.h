@@ -132,6 +132,14 @@ int sivo_stereo_hamming(int device, const sivo_keypoint* left, const uint8_t* de
                         const float* scale_factors, int nlevels, int rows, float min_d, float max_d,
                         int* best_idx, int* best_dist);
 
+/* The whole of Frame::ComputeStereoMatches (Frame.cc:444-629): Hamming search, 11x11 SAD slide (+-5 px) on the keypoint's
+ * pyramid level, parabola sub-pixel fit, disparity gate [0, mbf/mb), median-based outlier cut.  Uses the device-resident
+ * pyramids of the last sivo_orb_run of `left` / `right` (so mvImagePyramid need not travel to the host for it).
+ * u_right / depth: n_left floats each = mvRight / mvDepth (-1 where unmatched). */
+int sivo_stereo_match(const sivo_orb_t* left, const sivo_orb_t* right, const sivo_keypoint* kp_left, const uint8_t* desc_left,
+                      int n_left, const sivo_keypoint* kp_right, const uint8_t* desc_right, int n_right, float mb, float mbf,
+                      float* u_right, float* depth);
+
 /* ---- test hooks for single layers (float NCHW host arrays in/out; run the product kernels) ----- */
 int sivo_dbg_pool(int device, const float* in, int n, int c, int h, int w, float* out, int* mask);
 int sivo_dbg_unpool(int device, const float* in, const int* mask, int n, int c, int h, int w, float* out);

@@ -521,3 +521,90 @@ def extract(image: np.ndarray, params: ExtractorParams = ExtractorParams()) -> O
 def descriptor_distance(a: np.ndarray, b: np.ndarray) -> int:
     """ORBmatcher::DescriptorDistance (src/orbslam/ORBmatcher.cc:1582-1596): popcount of a XOR b."""
     return int(np.unpackbits(np.bitwise_xor(a, b)).sum())
+
+
+def compute_stereo_matches(kl, dl, kr, dr, pyr_l, pyr_r, scale, inv_scale, mb, mbf):
+    """Frame::ComputeStereoMatches (src/orbslam/Frame.cc:444-629) restated: row table, Hamming search with the octave
+    and disparity gates, 11x11 SAD slide on the keypoint's pyramid level, parabola fit, median-based outlier cut.
+    kl / kr: structured keypoint arrays (x, y, octave), dl / dr: [N, 32] u8, pyr_*: bordered level buffers.
+    Returns (mvRight, mvDepth) float32 arrays."""
+    f32 = np.float32
+    n_l = len(kl)
+    u_right = np.full(n_l, -1.0, f32)
+    depth = np.full(n_l, -1.0, f32)
+    rows = pyr_l[0].shape[0] - 2 * EDGE_THRESHOLD
+    table = [[] for _ in range(rows)]
+    for i in range(len(kr)):
+        r = f32(2.0) * scale[kr["octave"][i]]
+        lo, hi = int(np.floor(f32(kr["y"][i] - r))), int(np.ceil(f32(kr["y"][i] + r)))
+        for y in range(lo, hi + 1):
+            table[y].append(i)
+    th_orb = (100 + 50) // 2
+    min_d, max_d = f32(0), f32(f32(mbf) / f32(mb))
+    cand = []
+
+    def c_round(v):
+        return f32(np.floor(v + f32(0.5))) if v >= 0 else f32(-np.floor(-v + f32(0.5)))
+    for il in range(n_l):
+        ul, vl, lv = f32(kl["x"][il]), f32(kl["y"][il]), int(kl["octave"][il])
+        cands = table[int(vl)]
+        if not cands:
+            continue
+        min_u, max_u = f32(ul - max_d), f32(ul - min_d)
+        if max_u < 0:
+            continue
+        best, best_i = 100, 0
+        for j in cands:
+            if kr["octave"][j] < lv - 1 or kr["octave"][j] > lv + 1:
+                continue
+            if min_u <= kr["x"][j] <= max_u:
+                d = descriptor_distance(dl[il], dr[j])
+                if d < best:
+                    best, best_i = d, j
+        if best >= th_orb:
+            continue
+        sf = inv_scale[lv]
+        su_l, sv_l, su_r0 = c_round(f32(ul * sf)), c_round(f32(vl * sf)), c_round(f32(kr["x"][best_i] * sf))
+        img_l = pyr_l[lv][EDGE_THRESHOLD:-EDGE_THRESHOLD, EDGE_THRESHOLD:-EDGE_THRESHOLD].astype(np.int64)
+        img_r = pyr_r[lv][EDGE_THRESHOLD:-EDGE_THRESHOLD, EDGE_THRESHOLD:-EDGE_THRESHOLD].astype(np.int64)
+        w = 5
+        cy, cxl, cxr = int(sv_l), int(su_l), int(su_r0)
+        if su_r0 + 5 - 5 < 0 or su_r0 + 5 + 5 + 1 >= img_r.shape[1]:
+            continue
+        il_win = img_l[cy - w:cy + w + 1, cxl - w:cxl + w + 1]
+        il_win = il_win - il_win[w, w]
+        dists = []
+        for inc in range(-5, 6):
+            ir_win = img_r[cy - w:cy + w + 1, cxr + inc - w:cxr + inc + w + 1]
+            ir_win = ir_win - ir_win[w, w]
+            dists.append(int(np.abs(il_win - ir_win).sum()))
+        bd, binc = 2 ** 31 - 1, 0
+        for k, d in enumerate(dists):
+            if d < bd:
+                bd, binc = d, k - 5
+        if binc in (-5, 5):
+            continue
+        d1, d2, d3 = f32(dists[binc + 4]), f32(dists[binc + 5]), f32(dists[binc + 6])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            delta = f32(f32(d1 - d3) / f32(f32(2.0) * f32(f32(d1 + d3) - f32(f32(2.0) * d2))))
+        if delta < -1 or delta > 1 or np.isnan(delta):
+            continue
+        best_u = f32(scale[lv] * f32(f32(su_r0 + f32(binc)) + delta))
+        disp = f32(ul - best_u)
+        if min_d <= disp < max_d:
+            if disp <= 0:
+                disp = f32(0.01)
+                best_u = f32(float(ul) - 0.01)
+            depth[il] = f32(f32(mbf) / disp)
+            u_right[il] = best_u
+            cand.append((bd, il))
+    if cand:
+        cand.sort()
+        median = f32(cand[len(cand) // 2][0])
+        th = f32(1.5) * f32(1.4) * median
+        for d, il in reversed(cand):
+            if f32(d) < th:
+                break
+            u_right[il] = -1
+            depth[il] = -1
+    return u_right, depth

@@ -16,6 +16,8 @@ void set_last_error(const std::string& m) { g_last_error = m; }
 void stereo_hamming(int device, const sivo_keypoint* left, const uint8_t* dl, int nl, const sivo_keypoint* right,
                     const uint8_t* dr, int nr, const float* scale, int nlevels, int rows, float min_d, float max_d,
                     int* best_idx, int* best_dist);
+void stereo_match(const Orb& left, const Orb& right, const sivo_keypoint* kl, const uint8_t* dl, int nl, const sivo_keypoint* kr,
+                  const uint8_t* dr, int nr, float mb, float mbf, float* u_right, float* depth);
 }  // namespace sivo
 
 using namespace sivo;
@@ -210,6 +212,16 @@ int sivo_stereo_hamming(int device, const sivo_keypoint* left, const uint8_t* de
       fail(SIVO_EINVAL, "null argument");
     stereo_hamming(device, left, desc_left, n_left, right, desc_right, n_right, scale_factors, nlevels, rows, min_d, max_d,
                    best_idx, best_dist);
+  });
+}
+
+int sivo_stereo_match(const sivo_orb_t* left, const sivo_orb_t* right, const sivo_keypoint* kp_left, const uint8_t* desc_left,
+                      int n_left, const sivo_keypoint* kp_right, const uint8_t* desc_right, int n_right, float mb, float mbf,
+                      float* u_right, float* depth) {
+  return guarded([&] {
+    if (!left || !right || !u_right || !depth || (n_left && (!kp_left || !desc_left)) || (n_right && (!kp_right || !desc_right)))
+      fail(SIVO_EINVAL, "null argument");
+    stereo_match(*left->impl, *right->impl, kp_left, desc_left, n_left, kp_right, desc_right, n_right, mb, mbf, u_right, depth);
   });
 }
 

@@ -72,6 +72,11 @@ class Orb {
            uint8_t* const* pyr_out, const size_t* pyr_strides, bool gray_on_device = false);
   void level_size(int rows, int cols, int level, int* w, int* h) const;
   const OrbTables& tables() const { return tab_; }
+  // device-resident state of the last run, for the stereo stage (no host round trip of the pyramids)
+  const uint8_t* dev_pyramid() const { return d_pyr_.as<uint8_t>(); }
+  const OrbLevelTable& levels() const { return lt_; }
+  int device() const { return device_; }
+  bool has_run() const { return rows_ > 0; }
   int nlevels() const { return nlevels_; }
   void candidates(int level, int* xs, int* ys, int* resp, int cap, int* n) const;
   float device_ms = 0, tree_ms = 0;

@@ -3,7 +3,10 @@
 // [floor(vR - 2 s), ceil(vR + 2 s)] must contain int(vL), octave within +-1, uR in [uL - maxD, uL - minD];
 // distance = ORBmatcher::DescriptorDistance (ORBmatcher.cc:1582-1596) as 4 x __popcll.  The reference keeps
 // the first strictly smaller distance walking candidates in increasing iR, i.e. (min dist, min iR).
-#include "common.h"
+#include <algorithm>
+#include <vector>
+
+#include "orb.h"
 
 namespace sivo {
 namespace {
@@ -42,6 +45,106 @@ __global__ void k_stereo_hamming(const sivo_keypoint* __restrict__ kl, const uin
     best_idx[wid] = d < kThHigh ? static_cast<int>(best & 0xFFFFFu) : -1;
   }
 }
+
+// ---- the whole of Frame::ComputeStereoMatches (Frame.cc:444-629) for one left keypoint per warp: Hamming search as
+// above, then the 11x11 SAD slide over +-5 px on the keypoint's pyramid level (windows are centred-intensity
+// differences of u8 pixels, so every L1 distance is an exact integer), parabola sub-pixel fit, disparity gate.
+// The median-based outlier cut (:617-628) needs all matches and runs on the host over the returned SAD distances.
+__device__ __forceinline__ float c_roundf(float v) { return v >= 0.f ? floorf(__fadd_rn(v, 0.5f)) : -floorf(__fadd_rn(-v, 0.5f)); }
+
+__global__ void k_stereo_match(const sivo_keypoint* __restrict__ kl, const uint8_t* __restrict__ dl, int nl,
+                               const sivo_keypoint* __restrict__ kr, const uint8_t* __restrict__ dr, int nr,
+                               const float* __restrict__ scale, const float* __restrict__ inv_scale, const uint8_t* __restrict__ pyr_l,
+                               OrbLevelTable lt_l, const uint8_t* __restrict__ pyr_r, OrbLevelTable lt_r, float mb, float mbf,
+                               float* __restrict__ u_right, float* __restrict__ depth, int* __restrict__ sad_dist) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= nl) return;
+  const sivo_keypoint L = kl[wid];
+  const int rows = lt_l.lv[0].h;
+  const int row = static_cast<int>(L.y);
+  const float min_d = 0.f, max_d = __fdiv_rn(mbf, mb);
+  const float min_u = __fsub_rn(L.x, max_d), max_u = __fsub_rn(L.x, min_d);
+  const ulonglong4 a = *reinterpret_cast<const ulonglong4*>(dl + static_cast<size_t>(wid) * 32);
+  unsigned best = (static_cast<unsigned>(kThHigh) << 20) | 0xFFFFFu;
+  if (max_u >= 0.f && row >= 0 && row < rows) {
+    for (int i = lane; i < nr; i += 32) {
+      const sivo_keypoint R = kr[i];
+      const float band = __fmul_rn(2.0f, scale[R.octave]);
+      const int maxr = static_cast<int>(ceilf(__fadd_rn(R.y, band)));
+      const int minr = static_cast<int>(floorf(__fsub_rn(R.y, band)));
+      if (row < minr || row > maxr) continue;
+      if (R.octave < L.octave - 1 || R.octave > L.octave + 1) continue;
+      if (!(R.x >= min_u && R.x <= max_u)) continue;
+      const ulonglong4 b = *reinterpret_cast<const ulonglong4*>(dr + static_cast<size_t>(i) * 32);
+      unsigned d = __popcll(a.x ^ b.x) + __popcll(a.y ^ b.y) + __popcll(a.z ^ b.z) + __popcll(a.w ^ b.w);
+      if (d < static_cast<unsigned>(kThHigh)) best = min(best, (d << 20) | static_cast<unsigned>(i));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+  float out_u = -1.f, out_z = -1.f;
+  int out_sad = -1;
+  const int hd = best >> 20;
+  if (hd < (kThHigh + 50) / 2) {  // thOrbDist = (TH_HIGH + TH_LOW) / 2 (:448)
+    const int ir = best & 0xFFFFFu;
+    const int oct = L.octave;
+    const float sf = inv_scale[oct];
+    const float su_l = c_roundf(__fmul_rn(L.x, sf)), sv_l = c_roundf(__fmul_rn(L.y, sf)), su_r0 = c_roundf(__fmul_rn(kr[ir].x, sf));
+    const OrbLevel ll = lt_l.lv[oct], lr = lt_r.lv[oct];
+    const float iniu = su_r0 + 5.f - 5.f, endu = su_r0 + 5.f + 5.f + 1.f;
+    const int cx_l = static_cast<int>(su_l), cy = static_cast<int>(sv_l), cx_r = static_cast<int>(su_r0);
+    if (!(iniu < 0.f || endu >= static_cast<float>(lr.w)) && cx_l - 5 >= -kEdge && cx_l + 5 < ll.w + kEdge && cy - 5 >= -kEdge &&
+        cy + 5 < ll.h + kEdge) {
+      const uint8_t* pl = pyr_l + ll.img_off + static_cast<size_t>(cy + kEdge) * ll.pitch + cx_l + kEdge;
+      const uint8_t* pr = pyr_r + lr.img_off + static_cast<size_t>(cy + kEdge) * lr.pitch + cx_r + kEdge;
+      const int lc = pl[0];
+      int dists[11];
+#pragma unroll
+      for (int inc = -5; inc <= 5; ++inc) {
+        const int rc = pr[inc];
+        int s = 0;
+        for (int e = lane; e < 121; e += 32) {
+          const int dy = e / 11 - 5, dx = e % 11 - 5;
+          const int vl = static_cast<int>(pl[dy * ll.pitch + dx]) - lc;
+          const int vr = static_cast<int>(pr[dy * lr.pitch + dx + inc]) - rc;
+          s += abs(vl - vr);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        dists[inc + 5] = s;
+      }
+      int bd = 0x7fffffff, binc = 0;
+#pragma unroll
+      for (int i = 0; i < 11; ++i)
+        if (dists[i] < bd) { bd = dists[i]; binc = i - 5; }
+      if (binc != -5 && binc != 5) {
+        float d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+        for (int i = 1; i < 10; ++i)
+          if (i - 5 == binc) { d1 = static_cast<float>(dists[i - 1]); d2 = static_cast<float>(dists[i]); d3 = static_cast<float>(dists[i + 1]); }
+        const float delta = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
+        if (!(delta < -1.f || delta > 1.f)) {
+          float best_u = __fmul_rn(scale[oct], __fadd_rn(__fadd_rn(su_r0, static_cast<float>(binc)), delta));
+          float disp = __fsub_rn(L.x, best_u);
+          if (disp >= min_d && disp < max_d) {
+            if (disp <= 0.f) {
+              disp = 0.01f;
+              best_u = static_cast<float>(static_cast<double>(L.x) - 0.01);
+            }
+            out_z = __fdiv_rn(mbf, disp);
+            out_u = best_u;
+            out_sad = bd;
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    u_right[wid] = out_u;
+    depth[wid] = out_z;
+    sad_dist[wid] = out_sad;
+  }
+}
 }  // namespace
 
 void stereo_hamming(int device, const sivo_keypoint* left, const uint8_t* dl, int nl, const sivo_keypoint* right,
@@ -69,4 +172,49 @@ void stereo_hamming(int device, const sivo_keypoint* left, const uint8_t* dl, in
   SIVO_CUDA(cudaMemcpy(best_dist, d_bd.p, nl * sizeof(int), cudaMemcpyDeviceToHost));
 }
 
+}  // namespace sivo
+
+namespace sivo {
+// ComputeStereoMatches end to end; `left` / `right` are the extractors whose last runs produced the keypoints.
+void stereo_match(const Orb& left, const Orb& right, const sivo_keypoint* kl, const uint8_t* dl, int nl, const sivo_keypoint* kr,
+                  const uint8_t* dr, int nr, float mb, float mbf, float* u_right, float* depth) {
+  if (!left.has_run() || !right.has_run()) fail(SIVO_EINVAL, "stereo: run both extractors first");
+  if (left.device() != right.device() || left.nlevels() != right.nlevels()) fail(SIVO_EINVAL, "stereo: extractors differ");
+  if (nl < 0 || nr < 0 || nr >= (1 << 20) || !(mb > 0.f) || !(mbf > 0.f)) fail(SIVO_EINVAL, "stereo: bad arguments");
+  for (int i = 0; i < nl; ++i) { u_right[i] = -1.f; depth[i] = -1.f; }
+  if (nl == 0 || nr == 0) return;
+  const int nlev = left.nlevels();
+  for (int i = 0; i < nl; ++i) if (kl[i].octave < 0 || kl[i].octave >= nlev) fail(SIVO_EINVAL, "stereo: left octave out of range");
+  for (int i = 0; i < nr; ++i) if (kr[i].octave < 0 || kr[i].octave >= nlev) fail(SIVO_EINVAL, "stereo: right octave out of range");
+  SIVO_CUDA(cudaSetDevice(left.device()));
+  DevBuf d_kl(nl * sizeof(sivo_keypoint)), d_dl(static_cast<size_t>(nl) * 32), d_kr(nr * sizeof(sivo_keypoint)), d_dr(static_cast<size_t>(nr) * 32),
+      d_sc(nlev * sizeof(float)), d_isc(nlev * sizeof(float)), d_u(nl * sizeof(float)), d_z(nl * sizeof(float)), d_s(nl * sizeof(int));
+  SIVO_CUDA(cudaMemcpy(d_kl.p, kl, nl * sizeof(sivo_keypoint), cudaMemcpyHostToDevice));
+  SIVO_CUDA(cudaMemcpy(d_dl.p, dl, static_cast<size_t>(nl) * 32, cudaMemcpyHostToDevice));
+  SIVO_CUDA(cudaMemcpy(d_kr.p, kr, nr * sizeof(sivo_keypoint), cudaMemcpyHostToDevice));
+  SIVO_CUDA(cudaMemcpy(d_dr.p, dr, static_cast<size_t>(nr) * 32, cudaMemcpyHostToDevice));
+  SIVO_CUDA(cudaMemcpy(d_sc.p, left.tables().scale.data(), nlev * sizeof(float), cudaMemcpyHostToDevice));
+  SIVO_CUDA(cudaMemcpy(d_isc.p, left.tables().inv_scale.data(), nlev * sizeof(float), cudaMemcpyHostToDevice));
+  k_stereo_match<<<ceil_div(nl * 32, 128), 128>>>(d_kl.as<sivo_keypoint>(), d_dl.as<uint8_t>(), nl, d_kr.as<sivo_keypoint>(),
+                                                  d_dr.as<uint8_t>(), nr, d_sc.as<float>(), d_isc.as<float>(), left.dev_pyramid(),
+                                                  left.levels(), right.dev_pyramid(), right.levels(), mb, mbf, d_u.as<float>(),
+                                                  d_z.as<float>(), d_s.as<int>());
+  SIVO_CUDA(cudaGetLastError());
+  std::vector<int> sad(nl);
+  SIVO_CUDA(cudaMemcpy(u_right, d_u.p, nl * sizeof(float), cudaMemcpyDeviceToHost));
+  SIVO_CUDA(cudaMemcpy(depth, d_z.p, nl * sizeof(float), cudaMemcpyDeviceToHost));
+  SIVO_CUDA(cudaMemcpy(sad.data(), d_s.p, nl * sizeof(int), cudaMemcpyDeviceToHost));
+  // median-based outlier cut (Frame.cc:617-628)
+  std::vector<std::pair<int, int>> v;
+  for (int i = 0; i < nl; ++i) if (sad[i] >= 0) v.emplace_back(sad[i], i);
+  if (v.empty()) return;
+  std::sort(v.begin(), v.end());
+  const float median = static_cast<float>(v[v.size() / 2].first);
+  const float th = 1.5f * 1.4f * median;
+  for (int i = static_cast<int>(v.size()) - 1; i >= 0; --i) {
+    if (static_cast<float>(v[i].first) < th) break;
+    u_right[v[i].second] = -1.f;
+    depth[v[i].second] = -1.f;
+  }
+}
 }  // namespace sivo

@@ -124,3 +124,17 @@ def stereo_hamming(kp_left, desc_left, kp_right, desc_right, scale_factors, rows
                                         sf.ctypes.data_as(C.c_void_p), len(sf), rows, C.c_float(min_d), C.c_float(max_d),
                                         idx.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p)))
     return idx, dist
+
+
+def stereo_match(left: ORBextractor, right: ORBextractor, kp_left, desc_left, kp_right, desc_right, mb: float, mbf: float):
+    """Frame::ComputeStereoMatches on the device pyramids of the two extractors' last runs -> (mvRight, mvDepth)."""
+    kl = np.ascontiguousarray(kp_left, KP_DTYPE)
+    kr = np.ascontiguousarray(kp_right, KP_DTYPE)
+    dl = np.ascontiguousarray(desc_left, np.uint8)
+    dr = np.ascontiguousarray(desc_right, np.uint8)
+    u = np.empty(len(kl), np.float32)
+    z = np.empty(len(kl), np.float32)
+    L.check(L.lib().sivo_stereo_match(left._h, right._h, kl.ctypes.data_as(C.c_void_p), dl.ctypes.data_as(C.c_void_p), len(kl),
+                                      kr.ctypes.data_as(C.c_void_p), dr.ctypes.data_as(C.c_void_p), len(kr), C.c_float(mb),
+                                      C.c_float(mbf), u.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p)))
+    return u, z

@@ -120,3 +120,20 @@ def test_stereo_hamming_vs_brute_force():
         assert dist[i] == best and idx[i] == bi, i
         matched += bi >= 0
     assert matched > 200
+
+
+def test_stereo_match_full_vs_oracle():
+    """The whole ComputeStereoMatches (Hamming + SAD slide + parabola + median cut) on the device pyramids."""
+    from sivo_b200 import stereo_match
+    left, right = stereo_frame(1)
+    gl = np.ascontiguousarray(bgr_to_gray(left)[11:11 + 352, 109:109 + 1024])
+    gr = np.ascontiguousarray(bgr_to_gray(right)[11:11 + 352, 109:109 + 1024])
+    el, er = ORBextractor(2000, 1.2, 8, 20, 7), ORBextractor(2000, 1.2, 8, 20, 7)
+    kl, dl = el(gl, None)
+    kr, dr = er(gr, None)
+    mbf = 386.1448  # Camera.bf of config/kitti/KITTI00-02.yaml; mb = bf / fx
+    mb = mbf / 718.856
+    u, z = stereo_match(el, er, kl, dl, kr, dr, mb, mbf)
+    ru, rz = O.compute_stereo_matches(kl, dl, kr, dr, el._bordered, er._bordered, el.GetScaleFactors(), el.GetInverseScaleFactors(), mb, mbf)
+    assert np.array_equal(u, ru) and np.array_equal(z, rz)
+    assert (u >= 0).sum() > 150
