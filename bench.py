@@ -206,28 +206,25 @@ def main():
     d_cls = torch.empty(hw, dtype=torch.uint8, device=dev)
     d_conf = torch.empty(hw, dtype=torch.float64, device=dev)
     d_ent = torch.empty(hw, dtype=torch.float64, device=dev)
-    # packed per-frame record for the N>1 all-gather: classes u8 | conf f64 | entropy f64 | 2 x (count, kps, desc)
+    # packed per-frame record for the N>1 all-gather (sivo_b200/record.py)
+    from sivo_b200 import record
     kp_cap = args.nfeatures + 4 * 8 + 64
-    rec_bytes = hw * 17 + 2 * (8 + kp_cap * 60)
-    rec_bytes = (rec_bytes + 255) // 256 * 256
+    rec_bytes = record.record_bytes(hw, kp_cap)
+    offs = record.offsets(hw, kp_cap)
+    o_cls, o_conf, o_ent, o_kp = offs["classes"], offs["confidence"], offs["entropy"], offs["kp_left"]
     d_rec = torch.zeros(rec_bytes, dtype=torch.uint8, device=dev)
     d_all = torch.empty(rec_bytes * world, dtype=torch.uint8, device=dev) if world > 1 else None
-    h_kp = torch.empty(2 * (8 + kp_cap * 60), dtype=torch.uint8).pin_memory()
+    h_rec_t = torch.zeros(rec_bytes, dtype=torch.uint8).pin_memory()
+    h_rec = h_rec_t.numpy()
     stream = torch.cuda.current_stream(dev)
 
-    def pack_keypoints(kl, dl, kr, dr):
-        buf = h_kp.numpy()
-        off = 0
-        for k, d in ((kl, dl), (kr, dr)):
-            n = len(k)
-            buf[off:off + 8] = np.frombuffer(np.int64(n).tobytes(), np.uint8)
-            buf[off + 8:off + 8 + n * 28] = k.view(np.uint8).reshape(-1)[:n * 28]
-            buf[off + 8 + kp_cap * 28:off + 8 + kp_cap * 28 + n * 32] = d.reshape(-1)
-            off += 8 + kp_cap * 60
+    prof = {"segnet_launch": 0.0, "orb": 0.0, "pack": 0.0, "gather": 0.0}
 
     def device_step(i):
         j = i % n_frames
+        t0 = time.perf_counter()
         seg.run_device(d_bgr[j].data_ptr(), d_cls.data_ptr(), d_conf.data_ptr(), d_ent.data_ptr(), stream.cuda_stream)
+        t1 = time.perf_counter()
         out = [None, None]
 
         def right():
@@ -236,13 +233,22 @@ def main():
         t.start()
         out[0] = orb_l.run_device_input(d_gl[j].data_ptr(), NET_H, NET_W, NET_W)
         t.join()
+        t2 = time.perf_counter()
+        t3 = t2
         if world > 1:
-            pack_keypoints(out[0][0], out[0][1], out[1][0], out[1][1])
-            d_rec[:hw].copy_(d_cls, non_blocking=True)
-            d_rec[hw:hw * 9].copy_(d_conf.view(torch.uint8), non_blocking=True)
-            d_rec[hw * 9:hw * 17].copy_(d_ent.view(torch.uint8), non_blocking=True)
-            d_rec[hw * 17:hw * 17 + h_kp.numel()].copy_(h_kp, non_blocking=True)
+            record.pack_host_part(h_rec, hw, kp_cap, rank * 100000 + i, out[0][0], out[0][1], out[1][0], out[1][1])
+            t3 = time.perf_counter()
+            d_rec[:record.HEADER].copy_(h_rec_t[:record.HEADER], non_blocking=True)
+            d_rec[o_cls:o_cls + hw].copy_(d_cls, non_blocking=True)
+            d_rec[o_conf:o_conf + hw * 8].copy_(d_conf.view(torch.uint8), non_blocking=True)
+            d_rec[o_ent:o_ent + hw * 8].copy_(d_ent.view(torch.uint8), non_blocking=True)
+            d_rec[o_kp:].copy_(h_rec_t[o_kp:], non_blocking=True)
             dist.all_gather_into_tensor(d_all, d_rec)
+        t4 = time.perf_counter()
+        prof["segnet_launch"] += t1 - t0
+        prof["orb"] += t2 - t1
+        prof["pack"] += t3 - t2
+        prof["gather"] += t4 - t3
         return out
 
     def host_step(i):
@@ -343,6 +349,7 @@ def main():
                 "e2e": {"value": total_frames / e2e_elapsed, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu_base,
+                "host_ms_per_step": {k: round(1e3 * v / (args.steps + args.warmup), 3) for k, v in prof.items()},
                 "keypoints_last_frame": int(n_kp)}
         print(json.dumps(line))
     if world > 1:

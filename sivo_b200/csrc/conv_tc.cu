@@ -503,9 +503,14 @@ void conv_tc_dispatch(const ConvTcPlan& plan, cudaStream_t s, bool configure) {
 }  // namespace
 
 namespace {
-int tc_rows(int K, bool roll, int n_tile) { return (roll && n_tile <= 64) ? 4 : 2; }  // TMEM: 2 stages x rows x n_tile <= 512
+// Output rows per accumulator stage.  4 rows share each weight tile (TMEM: 2 stages x rows x n_tile <= 512 columns), but
+// a layer too small to give every SM a 4-row block runs 2-row blocks instead: twice the CTAs, half the work each.
+int tc_rows(int K, bool roll, int n_tile, int columns = 1 << 30, int H = 1 << 20) {
+  if (!(roll && n_tile <= 64)) return 2;
+  return static_cast<long>(columns) * ceil_div(H, 4) < 148 ? 2 : 4;
+}
 size_t tc_smem_bytes(int K, bool roll, int n_tile, int stages) {
-  const int rows = tc_rows(K, roll, n_tile);
+  const int rows = tc_rows(K, roll, n_tile);  // the 4-row variant is the larger footprint
   const int rk = rows + K - 1;
   const int slots = roll ? rk : 2 * rk;
   const int b_stride = (n_tile * 128 + 1023) & ~1023;
@@ -564,11 +569,11 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   p.chunks = in.cs / 64;
   p.out_f32 = out.dt == DType::F32;
   p.strips = ceil_div(in.w, 128);
-  const int rows = tc_rows(K, roll, n_tile);
-  const int total_pairs = ceil_div(in.h, rows);
   const int cout_tiles = p.out_f32 ? 1 : op.cout_p / n_tile;
-  // row blocks per CTA: minimise (waves of 148 SMs) x (blocks per CTA + ~1 block of prologue / halo overhead)
   const int columns = p.strips * in.n * cout_tiles;
+  const int rows = tc_rows(K, roll, n_tile, columns, in.h);
+  const int total_pairs = ceil_div(in.h, rows);
+  // row blocks per CTA: minimise (waves of 148 SMs) x (blocks per CTA + ~1 block of prologue / halo overhead)
   int ppc = 1;
   double best_cost = 1e30;
   for (int c = 1; c <= std::min(total_pairs, 24); ++c) {
