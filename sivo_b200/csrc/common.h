@@ -100,4 +100,13 @@ struct PinnedBuf {
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// true if `p` is page-locked host memory (cudaMallocHost / cudaHostRegister): async copies can then target the
+// caller's buffer directly instead of going through the library's own pinned staging buffers
+inline bool is_pinned_host(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 }  // namespace sivo

@@ -318,7 +318,12 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
   cudaStream_t s = stream_;
   const uint8_t* src = gray;
   size_t src_pitch = stride;
-  if (!gray_on_device) {
+  if (!gray_on_device && is_pinned_host(gray)) {  // page-locked caller image: no staging copy
+    SIVO_CUDA(cudaEventRecord(ev_[0], s));
+    SIVO_CUDA(cudaMemcpy2DAsync(d_gray_.p, cols, gray, stride, cols, rows, cudaMemcpyHostToDevice, s));
+    src = d_gray_.as<uint8_t>();
+    src_pitch = cols;
+  } else if (!gray_on_device) {
     uint8_t* hg = h_gray_.as<uint8_t>();
     for (int y = 0; y < rows; ++y) memcpy(hg + static_cast<size_t>(y) * cols, gray + static_cast<size_t>(y) * stride, cols);
     SIVO_CUDA(cudaEventRecord(ev_[0], s));
@@ -339,7 +344,20 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
   SIVO_CUDA(cudaEventRecord(ev_[1], s));
   // the blur and the pyramid read-back overlap the host quad tree
   orb_launch_blur(d_pyr_.as<uint8_t>(), d_blur_.as<uint8_t>(), lt_, s);
-  if (pyr_out) SIVO_CUDA(cudaMemcpyAsync(h_pyr_.p, d_pyr_.p, pyr_bytes_, cudaMemcpyDeviceToHost, s));
+  bool pyr_direct = pyr_out != nullptr;
+  if (pyr_out)
+    for (int l = 0; l < nlevels_; ++l) pyr_direct = pyr_direct && pyr_out[l] && is_pinned_host(pyr_out[l]);
+  if (pyr_out && pyr_direct) {  // page-locked level buffers (mvImagePyramid storage): strided copies straight into them
+    for (int l = 0; l < nlevels_; ++l) {
+      const OrbLevel& lv = lt_.lv[l];
+      const size_t dst_stride = pyr_strides ? pyr_strides[l] : static_cast<size_t>(lv.w + 2 * kEdge);
+      if (dst_stride < static_cast<size_t>(lv.w + 2 * kEdge)) fail(SIVO_EINVAL, "pyramid stride %zu too small for level %d", dst_stride, l);
+      SIVO_CUDA(cudaMemcpy2DAsync(pyr_out[l], dst_stride, d_pyr_.as<uint8_t>() + lv.img_off, lv.pitch, lv.w + 2 * kEdge,
+                                  lv.h + 2 * kEdge, cudaMemcpyDeviceToHost, s));
+    }
+  } else if (pyr_out) {
+    SIVO_CUDA(cudaMemcpyAsync(h_pyr_.p, d_pyr_.p, pyr_bytes_, cudaMemcpyDeviceToHost, s));
+  }
   launches = nlevels_ + 5;
   SIVO_CUDA(cudaEventSynchronize(ev_[1]));
 
@@ -416,7 +434,7 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
     if (kps) kps[i] = kp;
   }
   if (desc && total) memcpy(desc, h_desc_.p, static_cast<size_t>(total) * 32);
-  if (pyr_out) {
+  if (pyr_out && !pyr_direct) {
     for (int l = 0; l < nlevels_; ++l) {
       if (!pyr_out[l]) continue;
       const OrbLevel& lv = lt_.lv[l];

@@ -415,21 +415,28 @@ void SegNet::run_host(const uint8_t* bgr, int rows, int cols, size_t stride, uin
     y_tl = rows / 2 - H_ / 2;
   }
   SIVO_CUDA(cudaSetDevice(device_));
-  uint8_t* stage = h_in_.as<uint8_t>();
-  for (int y = 0; y < H_; ++y)
-    memcpy(stage + static_cast<size_t>(y) * W_ * 3, bgr + static_cast<size_t>(y + y_tl) * stride + static_cast<size_t>(x_tl) * 3,
-           static_cast<size_t>(W_) * 3);
   const size_t hw = static_cast<size_t>(H_) * W_;
-  SIVO_CUDA(cudaMemcpyAsync(d_bgr_.p, stage, hw * 3, cudaMemcpyHostToDevice, stream_));
+  const uint8_t* src = bgr + static_cast<size_t>(y_tl) * stride + static_cast<size_t>(x_tl) * 3;
+  if (is_pinned_host(bgr)) {  // crop straight out of the caller's page-locked image
+    SIVO_CUDA(cudaMemcpy2DAsync(d_bgr_.p, static_cast<size_t>(W_) * 3, src, stride, static_cast<size_t>(W_) * 3, H_,
+                                cudaMemcpyHostToDevice, stream_));
+  } else {
+    uint8_t* stage = h_in_.as<uint8_t>();
+    for (int y = 0; y < H_; ++y)
+      memcpy(stage + static_cast<size_t>(y) * W_ * 3, src + static_cast<size_t>(y) * stride, static_cast<size_t>(W_) * 3);
+    SIVO_CUDA(cudaMemcpyAsync(d_bgr_.p, stage, hw * 3, cudaMemcpyHostToDevice, stream_));
+  }
   run_device(d_bgr_.as<uint8_t>(), d_classes_.as<uint8_t>(), d_conf_.as<double>(), d_ent_.as<double>(), stream_);
-  if (classes) SIVO_CUDA(cudaMemcpyAsync(h_classes_.p, d_classes_.p, hw, cudaMemcpyDeviceToHost, stream_));
-  if (conf) SIVO_CUDA(cudaMemcpyAsync(h_conf_.p, d_conf_.p, hw * sizeof(double), cudaMemcpyDeviceToHost, stream_));
-  if (ent) SIVO_CUDA(cudaMemcpyAsync(h_ent_.p, d_ent_.p, hw * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  // outputs are caller-owned plain memory (Frame copies them into itself, Frame.cc:239-241): page-locked caller
+  // buffers receive the device copy directly, pageable ones go through the pinned staging buffers
+  const bool pc = is_pinned_host(classes), pf = is_pinned_host(conf), pe = is_pinned_host(ent);
+  if (classes) SIVO_CUDA(cudaMemcpyAsync(pc ? static_cast<void*>(classes) : h_classes_.p, d_classes_.p, hw, cudaMemcpyDeviceToHost, stream_));
+  if (conf) SIVO_CUDA(cudaMemcpyAsync(pf ? static_cast<void*>(conf) : h_conf_.p, d_conf_.p, hw * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  if (ent) SIVO_CUDA(cudaMemcpyAsync(pe ? static_cast<void*>(ent) : h_ent_.p, d_ent_.p, hw * sizeof(double), cudaMemcpyDeviceToHost, stream_));
   SIVO_CUDA(cudaStreamSynchronize(stream_));
-  // outputs are caller-owned plain memory (Frame copies them into itself, Frame.cc:239-241)
-  if (classes) memcpy(classes, h_classes_.p, hw);
-  if (conf) memcpy(conf, h_conf_.p, hw * sizeof(double));
-  if (ent) memcpy(ent, h_ent_.p, hw * sizeof(double));
+  if (classes && !pc) memcpy(classes, h_classes_.p, hw);
+  if (conf && !pf) memcpy(conf, h_conf_.p, hw * sizeof(double));
+  if (ent && !pe) memcpy(ent, h_ent_.p, hw * sizeof(double));
 }
 
 void SegNet::blob(const std::string& name, float* out, size_t cap, int* n, int* c, int* h, int* w) {

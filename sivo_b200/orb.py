@@ -42,7 +42,7 @@ class ORBextractor:
     def GetInverseScaleSigmaSquares(self): return self._is2.copy()
     def features_per_level(self): return self._per.copy()
 
-    def __call__(self, image: np.ndarray, mask=None, want_pyramid: bool = True):
+    def __call__(self, image: np.ndarray, mask=None, want_pyramid: bool = True, pyramid_buffers=None):
         """Returns (keypoints structured array KP_DTYPE, descriptors u8 [N,32]); fills mvImagePyramid with
         views at offset (19,19) into the bordered level buffers, like the reference's public member."""
         if image is None or image.size == 0:
@@ -64,7 +64,11 @@ class ORBextractor:
             for l in range(self.nlevels):
                 w, h = C.c_int(), C.c_int()
                 L.check(L.lib().sivo_orb_level_size(self._h, rows, cols, l, C.byref(w), C.byref(h)))
-                b = np.empty((h.value + 38, w.value + 38), np.uint8)
+                if pyramid_buffers is not None:  # caller-owned (e.g. page-locked) storage, reused across frames
+                    b = pyramid_buffers[l]
+                    assert b.shape == (h.value + 38, w.value + 38) and b.dtype == np.uint8
+                else:
+                    b = np.empty((h.value + 38, w.value + 38), np.uint8)
                 bufs.append(b)
                 ptrs[l] = b.ctypes.data
                 strides[l] = b.strides[0]
@@ -74,6 +78,15 @@ class ORBextractor:
         self._bordered = bufs
         self.mvImagePyramid = [b[19:-19, 19:-19] for b in bufs]
         return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def level_shapes(self, rows: int, cols: int):
+        """Bordered level buffer shapes (h + 38, w + 38) for a rows x cols image."""
+        out = []
+        for l in range(self.nlevels):
+            w, h = C.c_int(), C.c_int()
+            L.check(L.lib().sivo_orb_level_size(self._h, rows, cols, l, C.byref(w), C.byref(h)))
+            out.append((h.value + 38, w.value + 38))
+        return out
 
     def run_device_input(self, gray_ptr: int, rows: int, cols: int, pitch: int):
         cap = self.nfeatures + 4 * self.nlevels + 64

@@ -51,15 +51,23 @@ class BayesianSegNet:
     def set_profiling(self, on: bool):
         L.check(L.lib().sivo_segnet_set_profiling(self._h, int(on)))
 
-    def segmentImage(self, image: np.ndarray):
-        """image: HxWx3 u8 BGR.  Returns (classes u8 [H,W], confidence f64 [H,W], entropy f64 [H,W])."""
+    def segmentImage(self, image: np.ndarray, out=None):
+        """image: HxWx3 u8 BGR.  Returns (classes u8 [H,W], confidence f64 [H,W], entropy f64 [H,W]).
+        `out` = (classes, confidence, entropy) reuses caller buffers (like the Eigen matrices the C++ shim resizes
+        once); page-locked buffers receive the device copies directly."""
         if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
             raise ValueError("segmentImage expects an HxWx3 uint8 BGR image")
         if image.strides[2] != 1 or image.strides[1] != 3:
             image = np.ascontiguousarray(image)
-        classes = np.empty((self.height, self.width), np.uint8)
-        conf = np.empty((self.height, self.width), np.float64)
-        ent = np.empty((self.height, self.width), np.float64)
+        if out is not None:
+            classes, conf, ent = out
+            assert classes.shape == conf.shape == ent.shape == (self.height, self.width)
+            assert classes.dtype == np.uint8 and conf.dtype == np.float64 and ent.dtype == np.float64
+            assert classes.flags.c_contiguous and conf.flags.c_contiguous and ent.flags.c_contiguous
+        else:
+            classes = np.empty((self.height, self.width), np.uint8)
+            conf = np.empty((self.height, self.width), np.float64)
+            ent = np.empty((self.height, self.width), np.float64)
         L.check(L.lib().sivo_segnet_run(self._h, image.ctypes.data_as(C.c_void_p), image.shape[0], image.shape[1],
                                         C.c_size_t(image.strides[0]), classes.ctypes.data_as(C.c_void_p),
                                         conf.ctypes.data_as(C.c_void_p), ent.ctypes.data_as(C.c_void_p)))
