@@ -251,17 +251,34 @@ def main():
         prof["gather"] += t4 - t3
         return out
 
+    # e2e buffers: page-locked host memory, as the contract asks (inputs from pinned memory; the results land in
+    # caller-owned buffers the way the C++ shim's Eigen matrices / cv::Mat level buffers would)
+    def pinned_like(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+    keep = []
+    h_fr = []
+    for (left, gl, gr) in fr:
+        items = [pinned_like(x) for x in (left, gl, gr)]
+        keep.append(items)
+        h_fr.append(tuple(it[1] for it in items))
+    out_t = [torch.empty((NET_H, NET_W), dtype=torch.uint8).pin_memory(), torch.empty((NET_H, NET_W), dtype=torch.float64).pin_memory(),
+             torch.empty((NET_H, NET_W), dtype=torch.float64).pin_memory()]
+    out_np = tuple(t.numpy() for t in out_t)
+    pyr_t = [[torch.empty(shp, dtype=torch.uint8).pin_memory() for shp in orb_l.level_shapes(NET_H, NET_W)] for _ in range(2)]
+    pyr_np = [[t.numpy() for t in lst] for lst in pyr_t]
+
     def host_step(i):
         j = i % n_frames
-        left, gl, gr = fr[j]
-        res = seg.segmentImage(left)  # host image in, host maps out (H2D + D2H inside)
+        left, gl, gr = h_fr[j]
+        res = seg.segmentImage(left, out=out_np)  # host image in, host maps out (H2D + D2H inside)
         out = [None, None]
 
         def right():
-            out[1] = orb_r(gr, None, want_pyramid=True)
+            out[1] = orb_r(gr, None, want_pyramid=True, pyramid_buffers=pyr_np[1])
         t = threading.Thread(target=right)
         t.start()
-        out[0] = orb_l(gl, None, want_pyramid=True)
+        out[0] = orb_l(gl, None, want_pyramid=True, pyramid_buffers=pyr_np[0])
         t.join()
         return res, out
 
