@@ -277,6 +277,10 @@ __global__ void k_mc_reduce(const float* __restrict__ logits, int T, int cs, int
 // the final argmax / entropy are combined with xor-shuffles inside the 4-lane group (first maximum still wins).
 __global__ void k_mc_reduce_quad(const float* __restrict__ logits, int T, int C, int hw, uint8_t* __restrict__ classes,
                                  double* __restrict__ conf, double* __restrict__ entropy) {
+  // Instruction diet (ncu: the first version was issue-bound at 3400 instructions per warp, 0.8 TB/s): one IEEE
+  // reciprocal per sample instead of C divisions (p = e * (1/sum), <= 1 ulp from e/sum), mean = acc * (1/T) in double,
+  // and log2 evaluated in float on the double mean (relative error < 2^-22, i.e. < 1e-6 on the entropy, against the
+  // 1e-4 the contract allows); the products and the sums stay in double like computeEntropy (bayesian_segnet.cpp:38-44).
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int pix = gid >> 2, q = gid & 3;
   const bool live = pix < hw;
@@ -298,17 +302,19 @@ __global__ void k_mc_reduce_quad(const float* __restrict__ logits, int T, int C,
     }
     sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 1));
     sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 2));
+    const float inv = __frcp_rn(sum);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] += static_cast<double>(__fdiv_rn(x[j], sum));
+    for (int j = 0; j < 4; ++j) acc[j] += static_cast<double>(__fmul_rn(x[j], inv));
   }
+  const double inv_t = 1.0 / static_cast<double>(T);
   double best = -1.0, ent = 0.0;
   int arg = 0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     if (q * 4 + j >= C) continue;
-    const double pm = acc[j] / static_cast<double>(T);
+    const double pm = acc[j] * inv_t;
     if (pm > best) { best = pm; arg = q * 4 + j; }
-    if (pm != 0.0) ent += -1.0 * pm * log2(pm);
+    if (pm != 0.0) ent -= pm * static_cast<double>(log2f(static_cast<float>(pm)));
   }
 #pragma unroll
   for (int o = 1; o <= 2; o <<= 1) {
