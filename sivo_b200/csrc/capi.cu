@@ -368,6 +368,11 @@ int sivo_dbg_conv(int device, int engine, int precision, const float* in, int n,
     op.bn_shift.alloc(sh.size() * 4);
     SIVO_CUDA(cudaMemcpy(op.w_simt.p, ws.data(), ws.size() * 4, cudaMemcpyHostToDevice));
     SIVO_CUDA(cudaMemcpy(op.w_tc.p, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
+    if ((k == 7 || k == 3) && cin == 64 && cout == 64) {
+      std::vector<__half> wp = conv_tc_pair_weights(weight, k);
+      op.w_tc_pair.alloc(wp.size() * 2);
+      SIVO_CUDA(cudaMemcpy(op.w_tc_pair.p, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+    }
     SIVO_CUDA(cudaMemcpy(op.bias.p, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
     SIVO_CUDA(cudaMemcpy(op.bn_scale.p, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice));
     SIVO_CUDA(cudaMemcpy(op.bn_shift.p, sh.data(), sh.size() * 4, cudaMemcpyHostToDevice));

@@ -22,6 +22,7 @@
 
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "philox.cuh"
 #include "segnet.h"
@@ -158,6 +159,115 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// One output row of the epilogue for one thread (= one pixel x of row y): reads its accumulator columns from TMEM and
+// applies the runtime-selected tail (see the file header).  `trow` = TMEM address of this row's first column for the
+// thread's lane quarter, `n0` = first output channel of the CTA's tile.
+__device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t trow, const float* s_cls, int img, int y, int x, int n0) {
+    if (p.out_f32) {  // 16-channel float logits (the convolution feeding Softmax)
+      uint32_t v[32];
+      tmem_ld16(trow, v);
+      if (y < p.H && x < p.W) {
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float t = __fadd_rn(__uint_as_float(v[i]), __ldg(p.bias + i));
+          if (p.has_bn) t = __fadd_rn(__fmul_rn(t, __ldg(p.bn_scale + i)), __ldg(p.bn_shift + i));
+          if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
+          f[i] = t;
+        }
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+      }
+      return;
+    }
+    if (p.cls_w) {  // conv (+bias) -> half rounding (as the unfused path stores it) -> 1x1 classifier -> float logits
+      float l[16];
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) l[jj] = __ldg(p.cls_b + jj);
+      for (int cc = 0; cc < 64; cc += 32) {
+        uint32_t v[32];
+        tmem_ld32(trow + cc, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float t = __fadd_rn(__uint_as_float(v[i]), __ldg(p.bias + cc + i));
+          if (p.has_bn) t = __fadd_rn(__fmul_rn(t, __ldg(p.bn_scale + cc + i)), __ldg(p.bn_shift + cc + i));
+          if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
+          const float hv = __half2float(__float2half_rn(t));
+          const float4* w4 = reinterpret_cast<const float4*>(s_cls + (cc + i) * 16);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 w = w4[q4];
+            l[4 * q4] = fmaf(hv, w.x, l[4 * q4]);
+            l[4 * q4 + 1] = fmaf(hv, w.y, l[4 * q4 + 1]);
+            l[4 * q4 + 2] = fmaf(hv, w.z, l[4 * q4 + 2]);
+            l[4 * q4 + 3] = fmaf(hv, w.w, l[4 * q4 + 3]);
+          }
+        }
+      }
+      if (y < p.H && x < p.W) {
+        float4* dst = reinterpret_cast<float4*>(p.cls_out + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
+      }
+      return;
+    }
+    uint32_t bits[4] = {0, 0, 0, 0};
+    for (int cc = 0; cc < p.n_tile; cc += 32) {
+      uint32_t v[32];
+      tmem_ld32(trow + cc, v);
+      if (y < p.H && x < p.W) {
+        const int c0 = n0 + cc;
+        if (p.has_drop && ((c0 & 127) == 0 || cc == 0))
+          dropout_bits128(p.seed, *p.frame, p.drop_layer, img, static_cast<uint32_t>(y * p.W + x), c0 >> 7, bits);
+        const uint32_t keep = p.has_drop ? bits[(c0 >> 5) & 3] : 0xFFFFFFFFu;
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float f[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = c0 + i + e;
+            float t = __fadd_rn(__uint_as_float(v[i + e]), __ldg(p.bias + c));
+            if (p.has_bn) t = __fadd_rn(__fmul_rn(t, __ldg(p.bn_scale + c)), __ldg(p.bn_shift + c));
+            if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
+            f[e] = t;
+          }
+          __half2 h = __floats2half2_rn(f[0], f[1]);
+          if (p.has_drop) {  // y = x * keep * 2 on the stored half value (exact)
+            __half2 s = __floats2half2_rn((keep >> i) & 1u ? p.drop_scale : 0.f, (keep >> (i + 1)) & 1u ? p.drop_scale : 0.f);
+            h = __hmul2(h, s);
+          }
+          packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        if (p.unpool_mask) {
+          const uint4* mp = reinterpret_cast<const uint4*>(p.unpool_mask + ((static_cast<size_t>(img % p.mask_n) * p.H + y) * p.W + x) * p.cout_total + c0);
+          const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};  // 32 mask bytes, channel order
+#pragma unroll
+          for (int pos = 0; pos < 4; ++pos) {
+            uint32_t sel[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {  // half2 i holds channels 2i, 2i+1 -> mask bytes 2i, 2i+1
+              const uint32_t mb = mw[i >> 1] >> ((i & 1) * 16);
+              const uint32_t lo = ((mb & 0xFFu) == static_cast<uint32_t>(pos)) ? 0x0000FFFFu : 0u;
+              const uint32_t hi = (((mb >> 8) & 0xFFu) == static_cast<uint32_t>(pos)) ? 0xFFFF0000u : 0u;
+              sel[i] = packed[i] & (lo | hi);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) +
+                ((static_cast<size_t>(img) * 2 * p.H + 2 * y + (pos >> 1)) * (2 * p.W) + 2 * x + (pos & 1)) * p.cout_total + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(sel[4 * i], sel[4 * i + 1], sel[4 * i + 2], sel[4 * i + 3]);
+          }
+        } else {
+          uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout_total + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+        }
+      }
+    }
 }
 
 // ROLL = true : one 64-channel chunk (Cin == 64); halo rows persist in the ring while the CTA walks down its
@@ -334,109 +444,194 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       for (int r = 0; r < kRows; ++r) {
         const int y = y_base + j * kRows + r;
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
-        if (p.out_f32) {  // 16-channel float logits (the convolution feeding Softmax)
-          uint32_t v[32];
-          tmem_ld16(trow, v);
-          if (y < p.H && x < p.W) {
-            float f[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float t = __fadd_rn(__uint_as_float(v[i]), __ldg(p.bias + i));
-              if (p.has_bn) t = __fadd_rn(__fmul_rn(t, __ldg(p.bn_scale + i)), __ldg(p.bn_shift + i));
-              if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
-              f[i] = t;
-            }
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * 16);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        epilogue_row(p, trow, s_cls, img, y, x, n0);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + acc);
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Paired-tap variant (64 -> 64 channels, 4-row blocks).  With N = 64 every MMA re-reads its 16 KB A tile from shared
+// memory for 8 KB of weights: 192 B/clk of operand traffic against the SM's 128 B/clk, i.e. <= 67 % of the tensor
+// rate.  But output row r at tap row kh and output row r-1 at tap row kh+1 read the SAME input row, so with the four
+// accumulators laid out in decreasing row order one N = 128 MMA whose B tile stacks W(kh, kw) over W(kh+1, kw)
+// updates acc(r) | acc(r-1) from a single A read.  Per (tap-row pair, kw) that is 5 MMA groups (N = 64, 128, 128,
+// 128, 64) instead of 8: A traffic 80 KB instead of 128 KB per 1024 tensor cycles (141 B/clk), and 20 instead of 32
+// instructions.  Weights come as [kw][kh][cout][cin] so one TMA box of 128 rows lands both taps of a pair.
+template <int K>
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  constexpr int kRows = 4, RK = kRows + K - 1, kSlots = RK, kPad = (K - 1) / 2, NP = (K + 1) / 2;
+  constexpr int kBBytes = 128 * 128;  // two stacked 64 x 64 weight tiles
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* a_slots = smem;
+  uint8_t* b_stages = smem + kSlots * kSlotBytes;
+  const int kBStages = p.b_stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_stages + kBStages * kBBytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kSlots;
+  uint64_t* b_full = a_empty + kSlots;
+  uint64_t* b_empty = b_full + kBStages;
+  uint64_t* t_full = b_empty + kBStages;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  float* s_cls = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int strip = blockIdx.x % p.strips, rowblk = blockIdx.x / p.strips;
+  const int img = blockIdx.z;
+  const int x0 = strip * 128;
+  const int total_pairs = (p.H + kRows - 1) / kRows;
+  const int pair0 = rowblk * p.pairs_per_cta;
+  const int npairs = min(p.pairs_per_cta, total_pairs - pair0);
+  const int y_base = pair0 * kRows;
+  const int n_units = npairs * kRows + K - 1;
+  constexpr uint32_t tmem_cols = 512;  // 2 stages x 4 rows x 64 columns
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSlots; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < kBStages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (p.cls_w)
+    for (int e = threadIdx.x; e < 64 * 16; e += kTcThreads) s_cls[e] = p.cls_w[(e >> 4) * p.cls_stride + (e & 15)];
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+      for (int u = 0; u < n_units; ++u) {
+        const int slot = u % kSlots;
+        mbar_wait(a_empty + slot, ((static_cast<uint32_t>(u / kSlots)) & 1) ^ 1);
+        mbar_expect_tx(a_full + slot, static_cast<uint32_t>((128 + K - 1) * 128));
+        tma_load_4d(a_slots + slot * kSlotBytes, &map_a, a_full + slot, 0, x0 - kPad, y_base - kPad + u, img);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+      int st = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < npairs; ++j)
+        for (int pp = 0; pp < NP; ++pp)
+          for (int kw = 0; kw < K; ++kw) {
+            mbar_wait(b_empty + st, ph ^ 1);
+            mbar_expect_tx(b_full + st, static_cast<uint32_t>(kBBytes));
+            // rows (kw*K + 2pp)*64 .. +127 of the [kw][kh][cout] x cin matrix; the odd last tap row drags in 64 rows it
+            // never uses (the next kw's first tap, or zero fill past the end)
+            tma_load_3d(b_stages + st * kBBytes, &map_b, b_full + st, 0, (kw * K + 2 * pp) * 64, 0);
+            if (++st == kBStages) { st = 0; ph ^= 1; }
           }
-          continue;
+    }
+  } else if (warp == 2) {
+    // ===== MMA issuer (one warp: with N = 128 an MMA lasts 64 tensor cycles and costs 1-2 issue instructions) =====
+    const uint32_t idesc64 = (1u << 4) | (static_cast<uint32_t>(64 >> 3) << 17) | (8u << 24);
+    const uint32_t idesc128 = (1u << 4) | (static_cast<uint32_t>(128 >> 3) << 17) | (8u << 24);
+    const uint32_t a_base = smem_u32(a_slots), b_base = smem_u32(b_stages);
+    int st = 0;
+    uint32_t b_phase = 0;
+    int waited = 0;
+    for (int j = 0; j < npairs; ++j) {
+      const int acc = j & 1;
+      mbar_wait(t_empty + acc, ((j >> 1) & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int base_u = j * kRows;
+      const uint32_t d0 = tmem_base + static_cast<uint32_t>(acc * kRows * 64);  // column of acc(row 3); acc(r) sits at d0 + (3 - r) * 64
+      for (int pp = 0; pp < NP; ++pp) {
+        const int kh0 = 2 * pp;
+        const bool paired = kh0 + 1 < K;
+        const int last_unit = base_u + kh0 + (paired ? 1 : 0) + kRows - 1;
+        while (waited <= last_unit && waited < n_units) {
+          mbar_wait(a_full + waited % kSlots, (waited / kSlots) & 1);
+          ++waited;
         }
-        if (p.cls_w) {  // conv (+bias) -> half rounding (as the unfused path stores it) -> 1x1 classifier -> float logits
-          float l[16];
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t a_lo[kRows + 1];
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) l[jj] = __ldg(p.cls_b + jj);
-          for (int cc = 0; cc < 64; cc += 32) {
-            uint32_t v[32];
-            tmem_ld32(trow + cc, v);
+        for (int i = 0; i <= kRows; ++i)
+          a_lo[i] = (((a_base + ((base_u + kh0 + i) % kSlots) * kSlotBytes) & 0x3FFFFu) >> 4) | (1u << 16);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float t = __fadd_rn(__uint_as_float(v[i]), __ldg(p.bias + cc + i));
-              if (p.has_bn) t = __fadd_rn(__fmul_rn(t, __ldg(p.bn_scale + cc + i)), __ldg(p.bn_shift + cc + i));
-              if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
-              const float hv = __half2float(__float2half_rn(t));
-              const float4* w4 = reinterpret_cast<const float4*>(s_cls + (cc + i) * 16);
+        for (int kw = 0; kw < K; ++kw) {
+          mbar_wait(b_full + st, b_phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t b_lo = (((b_base + st * kBBytes) & 0x3FFFFu) >> 4) | (1u << 16);
+          if (elect_one()) {
+            const uint64_t hi = static_cast<uint64_t>(kDescHi) << 32;
+            if (pp == 0 && kw == 0) {
+              // first tap pair of the block: plain N = 64 MMAs so that each accumulator's first MMA can clear it
 #pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) {
-                const float4 w = w4[q4];
-                l[4 * q4] = fmaf(hv, w.x, l[4 * q4]);
-                l[4 * q4 + 1] = fmaf(hv, w.y, l[4 * q4 + 1]);
-                l[4 * q4 + 2] = fmaf(hv, w.z, l[4 * q4 + 2]);
-                l[4 * q4 + 3] = fmaf(hv, w.w, l[4 * q4 + 3]);
-              }
-            }
-          }
-          if (y < p.H && x < p.W) {
-            float4* dst = reinterpret_cast<float4*>(p.cls_out + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * 16);
+              for (int t = 0; t < 2; ++t)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_float4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
-          }
-          continue;
-        }
-        uint32_t bits[4] = {0, 0, 0, 0};
-        for (int cc = 0; cc < p.n_tile; cc += 32) {
-          uint32_t v[32];
-          tmem_ld32(trow + cc, v);
-          if (y < p.H && x < p.W) {
-            const int c0 = n0 + cc;
-            if (p.has_drop && ((c0 & 127) == 0 || cc == 0))
-              dropout_bits128(p.seed, *p.frame, p.drop_layer, img, static_cast<uint32_t>(y * p.W + x), c0 >> 7, bits);
-            const uint32_t keep = p.has_drop ? bits[(c0 >> 5) & 3] : 0xFFFFFFFFu;
-            uint32_t packed[16];
+                for (int r = 0; r < kRows; ++r)
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float f[2];
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16(d0 + (3 - r) * 64, hi | (a_lo[r + t] + 2 * k), hi | (b_lo + 512 * t + 2 * k), idesc64,
+                             static_cast<uint32_t>(t | k));
+            } else if (paired) {
 #pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int c = c0 + i + e;
-                float t = __fadd_rn(__uint_as_float(v[i + e]), __ldg(p.bias + c));
-                if (p.has_bn) t = __fadd_rn(__fmul_rn(t, __ldg(p.bn_scale + c)), __ldg(p.bn_shift + c));
-                if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
-                f[e] = t;
-              }
-              __half2 h = __floats2half2_rn(f[0], f[1]);
-              if (p.has_drop) {  // y = x * keep * 2 on the stored half value (exact)
-                __half2 s = __floats2half2_rn((keep >> i) & 1u ? p.drop_scale : 0.f, (keep >> (i + 1)) & 1u ? p.drop_scale : 0.f);
-                h = __hmul2(h, s);
-              }
-              packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            if (p.unpool_mask) {
-              const uint4* mp = reinterpret_cast<const uint4*>(p.unpool_mask + ((static_cast<size_t>(img % p.mask_n) * p.H + y) * p.W + x) * p.cout_total + c0);
-              const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
-              const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};  // 32 mask bytes, channel order
+              for (int k = 0; k < 4; ++k) umma_f16(d0 + 3 * 64, hi | (a_lo[0] + 8 * kw + 2 * k), hi | (b_lo + 2 * k), idesc64, 1u);
 #pragma unroll
-              for (int pos = 0; pos < 4; ++pos) {
-                uint32_t sel[16];
+              for (int i = 1; i < kRows; ++i)
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {  // half2 i holds channels 2i, 2i+1 -> mask bytes 2i, 2i+1
-                  const uint32_t mb = mw[i >> 1] >> ((i & 1) * 16);
-                  const uint32_t lo = ((mb & 0xFFu) == static_cast<uint32_t>(pos)) ? 0x0000FFFFu : 0u;
-                  const uint32_t hi = (((mb >> 8) & 0xFFu) == static_cast<uint32_t>(pos)) ? 0xFFFF0000u : 0u;
-                  sel[i] = packed[i] & (lo | hi);
-                }
-                uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) +
-                    ((static_cast<size_t>(img) * 2 * p.H + 2 * y + (pos >> 1)) * (2 * p.W) + 2 * x + (pos & 1)) * p.cout_total + c0);
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(d0 + (3 - i) * 64, hi | (a_lo[i] + 8 * kw + 2 * k), hi | (b_lo + 2 * k), idesc128, 1u);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(sel[4 * i], sel[4 * i + 1], sel[4 * i + 2], sel[4 * i + 3]);
-              }
+              for (int k = 0; k < 4; ++k) umma_f16(d0, hi | (a_lo[kRows] + 8 * kw + 2 * k), hi | (b_lo + 512 + 2 * k), idesc64, 1u);
             } else {
-              uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout_total + c0);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+              for (int r = 0; r < kRows; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(d0 + (3 - r) * 64, hi | (a_lo[r] + 8 * kw + 2 * k), hi | (b_lo + 2 * k), idesc64, 1u);
             }
+            umma_commit(b_empty + st);
           }
+          __syncwarp();
+          if (++st == kBStages) { st = 0; b_phase ^= 1; }
         }
+        // halo rows base_u + kh0 (and + kh0 + 1) are read by no later tap row of this block and by no later block
+        if (elect_one()) {
+          if (kh0 < kRows) umma_commit(a_empty + (base_u + kh0) % kSlots);
+          if (paired && kh0 + 1 < kRows) umma_commit(a_empty + (base_u + kh0 + 1) % kSlots);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) {
+        for (int i = K; i < kRows; ++i) umma_commit(a_empty + (base_u + i) % kSlots);  // K < 4: rows no tap row released
+        umma_commit(t_full + acc);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int x = x0 + q * 32 + lane;
+    for (int j = 0; j < npairs; ++j) {
+      const int acc = j & 1;
+      mbar_wait(t_full + acc, (j >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const int y = y_base + j * kRows + r;
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + (3 - r)) * 64);
+        epilogue_row(p, trow, s_cls, img, y, x, 0);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -484,6 +679,7 @@ struct ConvTcPlan {
   size_t smem;
   int k, rows;
   bool roll;
+  bool pair = false;  // paired-tap kernel (64 -> 64 channels, 4-row blocks)
 };
 
 namespace {
@@ -496,7 +692,8 @@ void conv_tc_dispatch(const ConvTcPlan& plan, cudaStream_t s, bool configure) {
     else kern<<<plan.grid, kTcThreads, plan.smem, s>>>(plan.map_a, plan.map_b, plan.p);
   };
   const int K = plan.k;
-  if (plan.roll && plan.rows == 4) { if (K == 7) go(k_conv_tc<7, true, 4>); else if (K == 3) go(k_conv_tc<3, true, 4>); else go(k_conv_tc<1, true, 4>); }
+  if (plan.pair) { if (K == 7) go(k_conv_tc_pair<7>); else go(k_conv_tc_pair<3>); }
+  else if (plan.roll && plan.rows == 4) { if (K == 7) go(k_conv_tc<7, true, 4>); else if (K == 3) go(k_conv_tc<3, true, 4>); else go(k_conv_tc<1, true, 4>); }
   else if (plan.roll) { if (K == 7) go(k_conv_tc<7, true, 2>); else if (K == 3) go(k_conv_tc<3, true, 2>); else go(k_conv_tc<1, true, 2>); }
   else { if (K == 3) go(k_conv_tc<3, false, 2>); else go(k_conv_tc<1, false, 2>); }
 }
@@ -593,6 +790,22 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   plan->grid = dim3(p.strips * ceil_div(total_pairs, ppc), cout_tiles, in.n);
   p.b_stages = tc_stages(K, roll, n_tile);
   plan->smem = tc_smem_bytes(K, roll, n_tile, p.b_stages);
+  const char* pair_env = std::getenv("SIVO_B200_TC_PAIR");
+  if (roll && rows == 4 && n_tile == 64 && op.cout_p == 64 && !p.out_f32 && (K == 7 || K == 3) && op.w_tc_pair.p &&
+      !(pair_env && pair_env[0] == '0')) {
+    // paired-tap kernel: weights as one [K*K*64 rows][64 cin] matrix in (kw, kh, cout) row order, 128-row boxes
+    cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(K) * K * 64, 1};
+    cuuint64_t strides[2] = {128, static_cast<cuuint64_t>(K) * K * 64 * 128};
+    cuuint32_t box[3] = {64, 128, 1};
+    encode(&plan->map_b, op.w_tc_pair.p, 3, dims, strides, box);
+    plan->pair = true;
+    const int slots = rows + K - 1;
+    int st = 6;
+    auto bytes = [&](int n) { return 1024 + static_cast<size_t>(slots) * kSlotBytes + static_cast<size_t>(n) * 16384 + (2 * slots + 2 * n + 4) * 8 + 16 + 64 * 16 * 4; };
+    while (st > 2 && bytes(st) > 227 * 1024) --st;
+    p.b_stages = st;
+    plan->smem = bytes(st);
+  }
   plan->k = K;
   plan->roll = roll;
   plan->rows = rows;
@@ -613,6 +826,18 @@ void conv_tc_set_unpool(ConvTcPlan& plan, const uint8_t* mask, int mask_n, void*
   plan.p.unpool_mask = mask;
   plan.p.mask_n = mask_n;
   plan.p.out = out_2h_2w;
+}
+
+std::vector<__half> conv_tc_pair_weights(const float* w_cout_cin_k_k, int K) {
+  // [kw][kh][cout = 64][cin = 64] half from Caffe's (cout, cin, kh, kw) float blob
+  std::vector<__half> out(static_cast<size_t>(K) * K * 64 * 64);
+  for (int kw = 0; kw < K; ++kw)
+    for (int kh = 0; kh < K; ++kh)
+      for (int co = 0; co < 64; ++co)
+        for (int ci = 0; ci < 64; ++ci)
+          out[((static_cast<size_t>(kw) * K + kh) * 64 + co) * 64 + ci] =
+              __float2half_rn(w_cout_cin_k_k[((static_cast<size_t>(co) * 64 + ci) * K + kh) * K + kw]);
+  return out;
 }
 
 bool conv_tc_can_fuse_classifier(const ConvTcPlan& plan) {

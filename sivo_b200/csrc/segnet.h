@@ -1,6 +1,8 @@
 // Bayesian SegNet executor: prototxt + caffemodel -> a static list of device ops over NHWC tensors.
 // Host-side twin of `SIVO::BayesianSegNet` (src/bayesian_segnet/bayesian_segnet.cpp).
 #pragma once
+#include <cuda_fp16.h>
+
 #include <map>
 #include <memory>
 #include <string>
@@ -34,7 +36,7 @@ struct Op {
   int expand_k = 0, expand_blk = 0;  // > 0: a KxK conv over 3 channels run as a 1x1 conv over the tap-expanded input
   bool relu = false, has_bn = false;
   float slope = 0.f;
-  DevBuf w_simt, w_tc, bias, bn_scale, bn_shift;
+  DevBuf w_simt, w_tc, w_tc_pair, bias, bn_scale, bn_shift;  // w_tc_pair: [kw][kh][cout][cin] half for the paired-tap kernel
   std::shared_ptr<ConvTcPlan> tc;
   bool use_tc = false;
   double flops = 0;  // algorithmic, for this op's batch
@@ -91,6 +93,8 @@ void conv_tc_set_dropout(ConvTcPlan& plan, uint64_t seed, const uint64_t* frame_
 void conv_tc_set_unpool(ConvTcPlan& plan, const uint8_t* mask, int mask_n, void* out_2h_2w);
 // fuses a following 1x1 convolution to <= 16 float logits (the layer feeding Softmax) into the epilogue
 bool conv_tc_can_fuse_classifier(const ConvTcPlan& plan);
+// host-side weight layout of the paired-tap kernel (64 -> 64 channels)
+std::vector<__half> conv_tc_pair_weights(const float* w_cout_cin_k_k, int K);
 void conv_tc_set_classifier(ConvTcPlan& plan, const float* w_cin_by_cout, int stride, const float* bias, float* logits);
 
 }  // namespace sivo
