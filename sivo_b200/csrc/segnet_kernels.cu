@@ -314,7 +314,8 @@ __global__ void k_mc_reduce_quad(const float* __restrict__ logits, int T, int C,
     if (q * 4 + j >= C) continue;
     const double pm = acc[j] * inv_t;
     if (pm > best) { best = pm; arg = q * 4 + j; }
-    if (pm != 0.0) ent -= pm * static_cast<double>(log2f(static_cast<float>(pm)));
+    const float pf = static_cast<float>(pm);  // a mean below the float range contributes < 1e-43 bits: same as the 0 log 0 := 0 rule
+    if (pf > 0.f) ent -= pm * static_cast<double>(log2f(pf));
   }
 #pragma unroll
   for (int o = 1; o <= 2; o <<= 1) {
