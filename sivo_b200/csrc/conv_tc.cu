@@ -792,7 +792,7 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   plan->smem = tc_smem_bytes(K, roll, n_tile, p.b_stages);
   const char* pair_env = std::getenv("SIVO_B200_TC_PAIR");
   if (roll && rows == 4 && n_tile == 64 && op.cout_p == 64 && !p.out_f32 && (K == 7 || K == 3) && op.w_tc_pair.p &&
-      !(pair_env && pair_env[0] == '0')) {
+      pair_env && pair_env[0] == '1') {  // opt-in: measured equal to the N = 64 kernel on B200 (profiles/r1_notes.md)
     // paired-tap kernel: weights as one [K*K*64 rows][64 cin] matrix in (kw, kh, cout) row order, 128-row boxes
     cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(K) * K * 64, 1};
     cuuint64_t strides[2] = {128, static_cast<cuuint64_t>(K) * K * 64 * 128};
