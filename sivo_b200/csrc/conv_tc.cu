@@ -59,6 +59,10 @@ struct TcParams {
   // lands in the 2x2 position its pooling mask names, zeros elsewhere (upsample_layer.cpp:74-103)
   const uint8_t* unpool_mask;
   int mask_n;
+  // 2x2/2 max pool with argmax fused into the epilogue (encoder convs): only the pooled tensor and its 2-bit mask are
+  // written (pooling_layer.cpp:140-187: scan (0,0),(0,1),(1,0),(1,1), strict '>', so the first maximum wins)
+  __half* pool_out;        // [N][H/2][W/2][cout_total]
+  uint8_t* pool_mask;      // same shape
   // 1x1 classifier fused into the epilogue (the layer feeding Softmax): logits[j] = cls_b[j] + sum_c half(out[c]) * cls_w[c][j];
   // the 64-channel output itself is then never written
   const float* cls_w;      // [64][cls_stride] float (half-rounded values), j < 16 used
@@ -215,6 +219,15 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t trow, c
       return;
     }
     uint32_t bits[4] = {0, 0, 0, 0};
+    // max-unpool: fetch the row's 2-bit mask codes for the first 64 channels before touching TMEM, so the (DRAM / L2)
+    // latency of the mask overlaps the accumulator loads instead of sitting in front of every 32-channel chunk
+    uint4 mrow[4] = {};
+    const bool inside = y < p.H && x < p.W;
+    if (p.unpool_mask && inside) {
+      const uint4* mp = reinterpret_cast<const uint4*>(p.unpool_mask + ((static_cast<size_t>(img % p.mask_n) * p.H + y) * p.W + x) * p.cout_total + n0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mrow[i] = __ldg(mp + i);
+    }
     for (int cc = 0; cc < p.n_tile; cc += 32) {
       uint32_t v[32];
       tmem_ld32(trow + cc, v);
@@ -243,8 +256,13 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t trow, c
           packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
         }
         if (p.unpool_mask) {
-          const uint4* mp = reinterpret_cast<const uint4*>(p.unpool_mask + ((static_cast<size_t>(img % p.mask_n) * p.H + y) * p.W + x) * p.cout_total + c0);
-          const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+          uint4 m0, m1;
+          if (cc == 0) { m0 = mrow[0]; m1 = mrow[1]; }
+              else if (cc == 32) { m0 = mrow[2]; m1 = mrow[3]; }
+          else {
+            const uint4* mp = reinterpret_cast<const uint4*>(p.unpool_mask + ((static_cast<size_t>(img % p.mask_n) * p.H + y) * p.W + x) * p.cout_total + c0);
+            m0 = __ldg(mp); m1 = __ldg(mp + 1);
+          }
           const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};  // 32 mask bytes, channel order
 #pragma unroll
           for (int pos = 0; pos < 4; ++pos) {
@@ -268,6 +286,62 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t trow, c
         }
       }
     }
+}
+
+// Two vertically adjacent output rows (y even) with the pooling epilogue: bias / BN / ReLU -> half (the value the
+// unfused path would store) -> 2x2 max with first-maximum argmax; the horizontal neighbour lives in the adjacent lane.
+__device__ __forceinline__ void epilogue_pool_rows(const TcParams& p, uint32_t trow0, uint32_t trow1, int img, int y, int x, int n0, int lane) {
+  const bool writer = (lane & 1) == 0 && y + 1 < p.H && x + 1 < p.W;
+  for (int cc = 0; cc < p.n_tile; cc += 32) {
+    uint32_t v0[32], v1[32];
+    tmem_ld32(trow0 + cc, v0);
+    tmem_ld32(trow1 + cc, v1);
+    const int c0 = n0 + cc;
+    uint32_t outv[16], outm[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) outm[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      __half2 h[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float f[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = c0 + i + e;
+          float t = __fadd_rn(__uint_as_float(r ? v1[i + e] : v0[i + e]), __ldg(p.bias + c));
+          if (p.has_bn) t = __fadd_rn(__fmul_rn(t, __ldg(p.bn_scale + c)), __ldg(p.bn_shift + c));
+          if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
+          f[e] = t;
+        }
+        h[r] = __floats2half2_rn(f[0], f[1]);
+      }
+      const uint32_t a = *reinterpret_cast<uint32_t*>(&h[0]), c = *reinterpret_cast<uint32_t*>(&h[1]);
+      const uint32_t b = __shfl_xor_sync(0xffffffffu, a, 1), d = __shfl_xor_sync(0xffffffffu, c, 1);
+      // window in scan order: a = (y, x), b = (y, x+1), c = (y+1, x), d = (y+1, x+1); two channels per register
+      uint32_t best = a, arg = 0;
+      const uint32_t cand[3] = {b, c, d};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const __half2 hb = *reinterpret_cast<const __half2*>(&best), hc = *reinterpret_cast<const __half2*>(&cand[k]);
+        const bool lo = __hgt(__low2half(hc), __low2half(hb)), hi = __hgt(__high2half(hc), __high2half(hb));
+        const uint32_t sel = (lo ? 0x0000FFFFu : 0u) | (hi ? 0xFFFF0000u : 0u);
+        best = (best & ~sel) | (cand[k] & sel);
+        arg = (arg & ~((lo ? 0xFFu : 0u) | (hi ? 0xFF00u : 0u))) | ((lo ? static_cast<uint32_t>(k + 1) : 0u) | (hi ? static_cast<uint32_t>(k + 1) << 8 : 0u));
+      }
+      outv[i >> 1] = best;
+      outm[i >> 2] |= arg << (((i >> 1) & 1) * 16);  // two mask bytes per half2, four per 32-bit word
+    }
+    if (writer) {
+      const size_t o = ((static_cast<size_t>(img) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * p.cout_total + c0;
+      uint4* dv = reinterpret_cast<uint4*>(p.pool_out + o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dv[i] = make_uint4(outv[4 * i], outv[4 * i + 1], outv[4 * i + 2], outv[4 * i + 3]);
+      uint4* dm = reinterpret_cast<uint4*>(p.pool_mask + o);
+      dm[0] = make_uint4(outm[0], outm[1], outm[2], outm[3]);
+      dm[1] = make_uint4(outm[4], outm[5], outm[6], outm[7]);
+    }
+  }
 }
 
 // ROLL = true : one 64-channel chunk (Cin == 64); halo rows persist in the ring while the CTA walks down its
@@ -440,11 +514,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       const int acc = j & 1;
       mbar_wait(t_full + acc, (j >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (p.pool_out) {
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) {
-        const int y = y_base + j * kRows + r;
-        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
-        epilogue_row(p, trow, s_cls, img, y, x, n0);
+        for (int r = 0; r < kRows; r += 2) {
+          const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
+          epilogue_pool_rows(p, trow, trow + p.n_tile, img, y_base + j * kRows + r, x, n0, lane);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          const int y = y_base + j * kRows + r;
+          const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
+          epilogue_row(p, trow, s_cls, img, y, x, n0);
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -627,11 +709,19 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int acc = j & 1;
       mbar_wait(t_full + acc, (j >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (p.pool_out) {
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) {
-        const int y = y_base + j * kRows + r;
-        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + (3 - r)) * 64);
-        epilogue_row(p, trow, s_cls, img, y, x, 0);
+        for (int r = 0; r < kRows; r += 2) {  // accumulators sit in decreasing row order: row r+1 is 64 columns below row r
+          const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + (3 - r)) * 64);
+          epilogue_pool_rows(p, trow, trow - 64, img, y_base + j * kRows + r, x, 0, lane);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          const int y = y_base + j * kRows + r;
+          const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + (3 - r)) * 64);
+          epilogue_row(p, trow, s_cls, img, y, x, 0);
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -786,6 +876,7 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   p.out = out.p;
   p.has_drop = 0; p.seed = 0; p.frame = nullptr; p.drop_layer = 0; p.drop_scale = 2.f;
   p.unpool_mask = nullptr; p.mask_n = 1;
+  p.pool_out = nullptr; p.pool_mask = nullptr;
   p.cls_w = nullptr; p.cls_b = nullptr; p.cls_out = nullptr; p.cls_stride = 0;
   plan->grid = dim3(p.strips * ceil_div(total_pairs, ppc), cout_tiles, in.n);
   p.b_stages = tc_stages(K, roll, n_tile);
@@ -840,8 +931,17 @@ std::vector<__half> conv_tc_pair_weights(const float* w_cout_cin_k_k, int K) {
   return out;
 }
 
+bool conv_tc_can_fuse_pool(const ConvTcPlan& plan) {
+  return !plan.p.out_f32 && !plan.p.unpool_mask && !plan.p.has_drop && !plan.p.cls_w && (plan.p.H % 2) == 0 && (plan.p.W % 2) == 0;
+}
+
+void conv_tc_set_pool(ConvTcPlan& plan, void* pooled, uint8_t* mask) {
+  plan.p.pool_out = static_cast<__half*>(pooled);
+  plan.p.pool_mask = mask;
+}
+
 bool conv_tc_can_fuse_classifier(const ConvTcPlan& plan) {
-  return plan.roll && plan.p.n_tile == 64 && plan.p.cout_total == 64 && !plan.p.out_f32 && !plan.p.unpool_mask && !plan.p.has_drop;
+  return plan.roll && plan.p.n_tile == 64 && plan.p.cout_total == 64 && !plan.p.out_f32 && !plan.p.unpool_mask && !plan.p.has_drop && !plan.p.pool_out;
 }
 
 void conv_tc_set_classifier(ConvTcPlan& plan, const float* w_cin_by_cout, int stride, const float* bias, float* logits) {

@@ -215,12 +215,21 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
       case LayerType::Pooling: {
         if ((iv.h | iv.w) & 1) fail(SIVO_EFORMAT, "layer '%s': odd input size %dx%d", ly.name.c_str(), iv.h, iv.w);
         if (iv.cs != iv.c) fail(SIVO_EFORMAT, "layer '%s': pooling a padded-channel tensor", ly.name.c_str());
+        const int pooled = add_tensor(ly.tops[0], iv.n, iv.c, iv.h / 2, iv.w / 2, iv.cs, act_);
+        const int pmask = add_tensor(ly.tops[1], iv.n, iv.c, iv.h / 2, iv.w / 2, iv.cs, act_, true);
+        if (!opt_.keep_blobs && !ops_.empty() && ops_.back().kind == Op::Conv && ops_.back().use_tc && ops_.back().out == in &&
+            iv.dt == DType::F16 && conv_tc_can_fuse_pool(*ops_.back().tc)) {
+          // the producing tensor-core convolution pools in its epilogue: the full-resolution activations are never stored
+          conv_tc_set_pool(*ops_.back().tc, tensors_[pooled]->v.p, tensors_[pmask]->buf.as<uint8_t>());
+          ops_.back().layer += "+" + ly.name;
+          break;
+        }
         Op op;
         op.kind = Op::Pool;
         op.layer = ly.name;
         op.in = in;
-        op.out = add_tensor(ly.tops[0], iv.n, iv.c, iv.h / 2, iv.w / 2, iv.cs, act_);
-        op.out2 = add_tensor(ly.tops[1], iv.n, iv.c, iv.h / 2, iv.w / 2, iv.cs, act_, true);
+        op.out = pooled;
+        op.out2 = pmask;
         ops_.push_back(std::move(op));
         break;
       }

@@ -91,6 +91,9 @@ void conv_tc_set_dropout(ConvTcPlan& plan, uint64_t seed, const uint64_t* frame_
 // fuses the max-unpool (Upsample) that consumes the convolution's output into its epilogue; `out_2h_2w` is the
 // unpooled tensor the convolution then writes instead of its own output
 void conv_tc_set_unpool(ConvTcPlan& plan, const uint8_t* mask, int mask_n, void* out_2h_2w);
+// fuses the 2x2/2 max pool (+ argmax mask) that consumes the convolution's output into its epilogue
+bool conv_tc_can_fuse_pool(const ConvTcPlan& plan);
+void conv_tc_set_pool(ConvTcPlan& plan, void* pooled, uint8_t* mask);
 // fuses a following 1x1 convolution to <= 16 float logits (the layer feeding Softmax) into the epilogue
 bool conv_tc_can_fuse_classifier(const ConvTcPlan& plan);
 // host-side weight layout of the paired-tap kernel (64 -> 64 channels)

@@ -198,11 +198,16 @@ def test_fused_epilogues_equal_the_unfused_ops(model_dir):
     classifier sums its 64 products in a different fp32 order, so logits agree to ~1e-6 relative."""
     net, w, proto, model = _full_model(model_dir)
     left, _ = stereo_frame(2)
-    res = []
+    res, pooled = [], []
     for keep in (True, False):
         seg = BayesianSegNet(BayesianSegNetParams(proto, model), seed=1234, T=2, precision="fp16", engine="auto", keep_blobs=keep)
         seg.set_frame(5)
         res.append(seg.segmentImage(left))
+        # pooled activations, argmax masks and unpooled tensors exist in both builds; fused or not they are the same arithmetic
+        pooled.append({n: seg.blob(n) for n in ("pool1", "pool1_mask", "pool2", "pool2_mask", "pool3_mask", "pool4", "pool4_mask",
+                                                "upsample3", "upsample1")})
+    for n in pooled[0]:
+        assert np.array_equal(pooled[0][n], pooled[1][n]), n
     (c0, f0, e0), (c1, f1, e1) = res
     assert (c0 != c1).mean() < 1e-4
     assert np.abs(e0 - e1).max() < 1e-2 and np.median(np.abs(e0 - e1)) < 1e-9
