@@ -333,24 +333,14 @@ SegNet::SegNet(const std::string& prototxt, const std::string& caffemodel, const
 
 SegNet::~SegNet() {
   cudaSetDevice(device_);
+  if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
   for (auto e : events_) cudaEventDestroy(e);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
-void SegNet::run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_dev, double* ent_dev, cudaStream_t s) {
-  SIVO_CUDA(cudaSetDevice(device_));
-  if (!s) s = stream_;
-  *h_frame_.as<uint64_t>() = frame_++;
-  SIVO_CUDA(cudaMemcpyAsync(d_frame_.p, h_frame_.p, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-  if (profiling_ && events_.size() < ops_.size() + 1) {
-    while (events_.size() < ops_.size() + 1) {
-      cudaEvent_t e;
-      SIVO_CUDA(cudaEventCreate(&e));
-      events_.push_back(e);
-    }
-  }
+void SegNet::enqueue(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_dev, double* ent_dev, cudaStream_t s, bool timed) {
   launches = 0;
-  if (profiling_) SIVO_CUDA(cudaEventRecord(events_[0], s));
+  if (timed) SIVO_CUDA(cudaEventRecord(events_[0], s));
   for (size_t i = 0; i < ops_.size(); ++i) {
     Op& op = ops_[i];
     switch (op.kind) {
@@ -401,9 +391,22 @@ void SegNet::run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* co
       }
     }
     ++launches;
-    if (profiling_) SIVO_CUDA(cudaEventRecord(events_[i + 1], s));
+    if (timed) SIVO_CUDA(cudaEventRecord(events_[i + 1], s));
   }
+}
+
+void SegNet::run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_dev, double* ent_dev, cudaStream_t s) {
+  SIVO_CUDA(cudaSetDevice(device_));
+  if (!s) s = stream_;
+  *h_frame_.as<uint64_t>() = frame_++;
+  SIVO_CUDA(cudaMemcpyAsync(d_frame_.p, h_frame_.p, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
   if (profiling_) {
+    while (events_.size() < ops_.size() + 1) {
+      cudaEvent_t e;
+      SIVO_CUDA(cudaEventCreate(&e));
+      events_.push_back(e);
+    }
+    enqueue(bgr_dev, classes_dev, conf_dev, ent_dev, s, true);
     SIVO_CUDA(cudaEventSynchronize(events_[ops_.size()]));
     conv_ms = other_ms = reduce_ms = 0;
     for (size_t i = 0; i < ops_.size(); ++i) {
@@ -414,7 +417,46 @@ void SegNet::run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* co
       else other_ms += ms;
     }
     SIVO_CUDA(cudaEventElapsedTime(&total_ms, events_[0], events_[ops_.size()]));
+    return;
   }
+  // Steady state: the whole op list is one CUDA graph launch.  Everything that changes per frame lives in device
+  // memory (the frame counter read by the dropout code), so the captured kernels and their arguments never change.
+  bool all_tc = true;
+  for (const Op& op : ops_) if (op.kind == Op::Conv && !op.use_tc) all_tc = false;  // the SIMT launcher sets attributes per launch
+  static const bool graphs_enabled = [] { const char* e = std::getenv("SIVO_B200_NO_GRAPH"); return !(e && e[0] == '1'); }();
+  if (graphs_enabled && graph_ok_ && all_tc) {
+    const void* key[5] = {bgr_dev, classes_dev, conf_dev, ent_dev, s};
+    if (!graph_exec_ || memcmp(key, graph_key_, sizeof key) != 0) {
+      if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+      cudaGraph_t g = nullptr;
+      cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+      if (e == cudaSuccess) {
+        try {
+          enqueue(bgr_dev, classes_dev, conf_dev, ent_dev, s, false);
+        } catch (...) {
+          cudaStreamEndCapture(s, &g);
+          if (g) cudaGraphDestroy(g);
+          graph_ok_ = false;
+          throw;
+        }
+        e = cudaStreamEndCapture(s, &g);
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&graph_exec_, g, 0);
+        if (g) cudaGraphDestroy(g);
+      }
+      if (e != cudaSuccess) {  // fall back to plain launches for this handle
+        cudaGetLastError();
+        graph_ok_ = false;
+        graph_exec_ = nullptr;
+      } else {
+        memcpy(graph_key_, key, sizeof key);
+      }
+    }
+    if (graph_exec_) {
+      SIVO_CUDA(cudaGraphLaunch(graph_exec_, s));
+      return;
+    }
+  }
+  enqueue(bgr_dev, classes_dev, conf_dev, ent_dev, s, false);
 }
 
 void SegNet::run_host(const uint8_t* bgr, int rows, int cols, size_t stride, uint8_t* classes, double* conf, double* ent) {

@@ -66,6 +66,7 @@ class SegNet {
   int add_tensor(const std::string& name, int n, int c, int h, int w, int cs, DType dt, bool mask = false);
   void build(const NetSpec& net, const WeightMap& weights);
   void prepare_conv(Op& op, const std::vector<Blob>& conv_blobs, const std::vector<Blob>* bn_blobs);
+  void enqueue(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_dev, double* ent_dev, cudaStream_t s, bool timed);
 
   sivo_segnet_options opt_;
   int device_ = 0, T_ = 0, H_ = 0, W_ = 0, n_classes_ = 0;
@@ -80,6 +81,10 @@ class SegNet {
   DevBuf d_bgr_, d_classes_, d_conf_, d_ent_, d_frame_;
   PinnedBuf h_in_, h_classes_, h_conf_, h_ent_, h_frame_;
   std::vector<cudaEvent_t> events_;
+  // the op list captured once as a CUDA graph (one launch per frame); re-captured if the buffers or the stream change
+  cudaGraphExec_t graph_exec_ = nullptr;
+  const void* graph_key_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool graph_ok_ = true;
 };
 
 // conv_tc.cu -- tcgen05 implicit-GEMM convolution
