@@ -40,6 +40,7 @@ struct TcParams {
   int cout_total;          // channel stride of the output tensor
   int n_tile;              // UMMA N (16 for the float logits layer, else 64 or 128)
   int chunks;              // Cin / 64
+  int dbg_noshift;         // timing experiment only: ignore the kw shift of the A operand (wrong results)
   int b_stages;            // weight ring depth (as many of kMaxBStages as fit in shared memory)
   int out_f32;             // 1: 16-channel float output (logits)
   int pairs_per_cta;       // row blocks (R output rows each) one CTA walks
@@ -470,6 +471,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             d_row[m] = tmem_base + static_cast<uint32_t>((acc * kRows + r_first + m) * p.n_tile);
           }
           const uint32_t first_row = (ch | kh) ? 1u : 0u;
+          const uint32_t kw_step = p.dbg_noshift ? 0u : 8u;
 #pragma unroll
           for (int kw = 0; kw < K; ++kw) {
             mbar_wait(b_full + st, b_phase);
@@ -482,7 +484,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               for (int m = 0; m < kMine; ++m) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_f16(d_row[m], (static_cast<uint64_t>(kDescHi) << 32) | (a_row_lo[m] + 8 * kw + 2 * k),
+                  umma_f16(d_row[m], (static_cast<uint64_t>(kDescHi) << 32) | (a_row_lo[m] + kw_step * kw + 2 * k),
                            (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k), idesc, first_row | static_cast<uint32_t>(kw | k));
               }
               umma_commit(b_empty + st);  // weight stage is free once both issuers' MMAs retire
@@ -876,6 +878,8 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   p.out = out.p;
   p.has_drop = 0; p.seed = 0; p.frame = nullptr; p.drop_layer = 0; p.drop_scale = 2.f;
   p.unpool_mask = nullptr; p.mask_n = 1;
+  p.dbg_noshift = 0;
+  if (const char* e = std::getenv("SIVO_B200_TC_NOSHIFT")) p.dbg_noshift = e[0] == '1';
   p.pool_out = nullptr; p.pool_mask = nullptr;
   p.cls_w = nullptr; p.cls_b = nullptr; p.cls_out = nullptr; p.cls_stride = 0;
   plan->grid = dim3(p.strips * ceil_div(total_pairs, ppc), cout_tiles, in.n);
