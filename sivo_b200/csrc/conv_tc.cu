@@ -480,10 +480,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             // advances it by 32 B >> 4 = 2, a tap column by 128 B >> 4 = 8
             const uint32_t b_lo = (((b_base + st * b_stride) & 0x3FFFFu) >> 4) | (1u << 16);
             if (elect_one()) {
+              // K step outer, row inner: consecutive MMAs go to different accumulators (an MMA chain on one
+              // accumulator is serialised by the accumulate dependency; see profiles/r1_notes.md)
 #pragma unroll
-              for (int m = 0; m < kMine; ++m) {
+              for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                for (int m = 0; m < kMine; ++m)
                   umma_f16(d_row[m], (static_cast<uint64_t>(kDescHi) << 32) | (a_row_lo[m] + kw_step * kw + 2 * k),
                            (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k), idesc, first_row | static_cast<uint32_t>(kw | k));
               }
