@@ -367,6 +367,7 @@ def main():
                         "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu_base,
                 "host_ms_per_step": {k: round(1e3 * v / (args.steps + args.warmup), 3) for k, v in prof.items()},
+                "orb_last_call": {"left": orb_l.last_timing(), "right": orb_r.last_timing()},
                 "keypoints_last_frame": int(n_kp)}
         print(json.dumps(line))
     if world > 1:
