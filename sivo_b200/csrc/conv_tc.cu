@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -40,6 +41,7 @@ struct TcParams {
   int cout_total;          // channel stride of the output tensor
   int n_tile;              // UMMA N (16 for the float logits layer, else 64 or 128)
   int chunks;              // Cin / 64
+  int w_rep;               // weight tensor replicas in global memory (spreads the L2 hot spot all CTAs hammer)
   int dbg_noshift;         // timing experiment only: ignore the kw shift of the A operand (wrong results)
   int b_stages;            // weight ring depth (as many of kMaxBStages as fit in shared memory)
   int out_f32;             // 1: 16-channel float output (logits)
@@ -429,6 +431,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     // ===== weight producer =====
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+      const int w_replica = static_cast<int>((blockIdx.x + blockIdx.z) % static_cast<unsigned>(p.w_rep));
       uint32_t it = 0;
       for (int j = 0; j < npairs; ++j)
         for (int ch = 0; ch < NC; ++ch)
@@ -436,7 +439,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             const int st = it % kBStages;
             mbar_wait(b_empty + st, ((it / kBStages) & 1) ^ 1);
             mbar_expect_tx(b_full + st, static_cast<uint32_t>(b_bytes));
-            tma_load_3d(b_stages + st * b_stride, &map_b, b_full + st, ch * 64, n0, tap);
+            tma_load_3d(b_stages + st * b_stride, &map_b, b_full + st, ch * 64, n0, tap + w_replica * K * K);
           }
     }
   } else if (warp == 2 || warp == 3) {
@@ -614,6 +617,7 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+      const int w_replica = static_cast<int>((blockIdx.x + blockIdx.z) % static_cast<unsigned>(p.w_rep));
       int st = 0;
       uint32_t ph = 0;
       for (int j = 0; j < npairs; ++j)
@@ -623,7 +627,7 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_expect_tx(b_full + st, static_cast<uint32_t>(kBBytes));
             // rows (kw*K + 2pp)*64 .. +127 of the [kw][kh][cout] x cin matrix; the odd last tap row drags in 64 rows it
             // never uses (the next kw's first tap, or zero fill past the end)
-            tma_load_3d(b_stages + st * kBBytes, &map_b, b_full + st, 0, (kw * K + 2 * pp) * 64, 0);
+            tma_load_3d(b_stages + st * kBBytes, &map_b, b_full + st, 0, (kw * K + 2 * pp) * 64, w_replica);
             if (++st == kBStages) { st = 0; ph ^= 1; }
           }
     }
@@ -774,6 +778,7 @@ struct ConvTcPlan {
   int k, rows;
   bool roll;
   bool pair = false;  // paired-tap kernel (64 -> 64 channels, 4-row blocks)
+  DevBuf w_replicas;  // private replicated copy of the weights (w_rep > 1)
 };
 
 namespace {
@@ -847,17 +852,28 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
     encode(&plan->map_a, in.p, 4, dims, strides, box);
   }
   const int n_tile = tc_pick_n(op, out, roll);
-  {  // weights: [tap][cout_p][cin_p] half, dims (cin, cout, tap)
-    cuuint64_t dims[3] = {static_cast<cuuint64_t>(op.cin_p), static_cast<cuuint64_t>(op.cout_p), static_cast<cuuint64_t>(K * K)};
+  int w_rep = 1;
+  if (const char* e = std::getenv("SIVO_B200_TC_WREP")) w_rep = std::max(1, std::min(16, atoi(e)));
+  {  // weights: [replica][tap][cout_p][cin_p] half, dims (cin, cout, replica * tap)
+    const size_t one = static_cast<size_t>(K) * K * op.cout_p * op.cin_p * 2;
+    void* wbase = const_cast<void*>(w_tc);
+    if (w_rep > 1) {
+      plan->w_replicas.alloc(one * w_rep);
+      for (int r = 0; r < w_rep; ++r)
+        SIVO_CUDA(cudaMemcpy(plan->w_replicas.as<uint8_t>() + r * one, w_tc, one, cudaMemcpyDeviceToDevice));
+      wbase = plan->w_replicas.p;
+    }
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(op.cin_p), static_cast<cuuint64_t>(op.cout_p), static_cast<cuuint64_t>(K * K * w_rep)};
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(op.cin_p) * 2, static_cast<cuuint64_t>(op.cout_p) * op.cin_p * 2};
     cuuint32_t box[3] = {64, static_cast<cuuint32_t>(n_tile), 1};
-    encode(&plan->map_b, const_cast<void*>(w_tc), 3, dims, strides, box);
+    encode(&plan->map_b, wbase, 3, dims, strides, box);
   }
   TcParams& p = plan->p;
   p.H = in.h; p.W = in.w; p.N_batch = in.n;
   p.cout_total = out.cs;
   p.n_tile = n_tile;
   p.chunks = in.cs / 64;
+  p.w_rep = w_rep;
   p.out_f32 = out.dt == DType::F32;
   p.strips = ceil_div(in.w, 128);
   const int cout_tiles = p.out_f32 ? 1 : op.cout_p / n_tile;
@@ -891,10 +907,18 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   if (roll && rows == 4 && n_tile == 64 && op.cout_p == 64 && !p.out_f32 && (K == 7 || K == 3) && op.w_tc_pair.p &&
       pair_env && pair_env[0] == '1') {  // opt-in: measured equal to the N = 64 kernel on B200 (profiles/r1_notes.md)
     // paired-tap kernel: weights as one [K*K*64 rows][64 cin] matrix in (kw, kh, cout) row order, 128-row boxes
-    cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(K) * K * 64, 1};
-    cuuint64_t strides[2] = {128, static_cast<cuuint64_t>(K) * K * 64 * 128};
+    const size_t one = static_cast<size_t>(K) * K * 64 * 128;
+    void* wbase = op.w_tc_pair.p;
+    if (w_rep > 1) {
+      plan->w_replicas.alloc(one * w_rep);
+      for (int r = 0; r < w_rep; ++r)
+        SIVO_CUDA(cudaMemcpy(plan->w_replicas.as<uint8_t>() + r * one, op.w_tc_pair.p, one, cudaMemcpyDeviceToDevice));
+      wbase = plan->w_replicas.p;
+    }
+    cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(K) * K * 64, static_cast<cuuint64_t>(w_rep)};
+    cuuint64_t strides[2] = {128, one};
     cuuint32_t box[3] = {64, 128, 1};
-    encode(&plan->map_b, op.w_tc_pair.p, 3, dims, strides, box);
+    encode(&plan->map_b, wbase, 3, dims, strides, box);
     plan->pair = true;
     const int slots = rows + K - 1;
     int st = 6;
