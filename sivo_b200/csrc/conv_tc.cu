@@ -305,7 +305,6 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t trow, c
 // because the epilogue then outlasts the next block's MMAs.  Here the 128 epilogue threads write their pixel's 128 bytes
 // into a 16 KB swizzled staging tile (conflict-free st.shared) and one thread issues a single bulk tensor store per row;
 // rows / pixels outside the image are clipped by the TMA unit.  `tq` = pixel index inside the 128-px strip.
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
                "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -314,10 +313,13 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-__device__ __forceinline__ void epilogue_row_tma(const TcParams& p, const CUtensorMap* map_o, uint8_t* stage, uint32_t trow, const float* s_cls,
-                                                 int img, int y, int x0, int tq, int n0) {
-  if (y >= p.H) return;  // uniform over the 128 epilogue threads
-  const int x = x0 + tq;
+// Each epilogue warp owns a 4 KB slice of the staging tile (its 32 pixels x 128 B) and its own bulk-store stream, so the
+// four warps never wait for each other: lane 0 waits for the warp's previous store to have read the slice, the warp
+// fills it, lane 0 issues the next store.  `wstage` = this warp's slice, `xw` = first pixel of the warp's 32-px span.
+__device__ __forceinline__ void epilogue_row_tma(const TcParams& p, const CUtensorMap* map_o, uint8_t* wstage, uint32_t trow, const float* s_cls,
+                                                 int img, int y, int xw, int lane, int n0) {
+  if (y >= p.H) return;  // warp-uniform
+  const int x = xw + lane;
   if (p.cls_w) {  // 1x1 classifier: 16 float logits per pixel, 64 B rows, no swizzle
     float l[16];
 #pragma unroll
@@ -342,14 +344,14 @@ __device__ __forceinline__ void epilogue_row_tma(const TcParams& p, const CUtens
         }
       }
     }
-    if (tq == 0) tma_store_wait_read();
-    epi_bar();
-    float4* dst = reinterpret_cast<float4*>(stage + tq * 64);
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+    float4* dst = reinterpret_cast<float4*>(wstage + lane * 64);
 #pragma unroll
     for (int i = 0; i < 4; ++i) dst[i] = make_float4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    epi_bar();
-    if (tq == 0) tma_store_4d(map_o, stage, 0, x0, y, img);
+    __syncwarp();
+    if (lane == 0) tma_store_4d(map_o, wstage, 0, xw, y, img);
     return;
   }
   // 64 channels of this pixel as 32 half2 words: bias / BN / ReLU / (dropout)
@@ -389,30 +391,30 @@ __device__ __forceinline__ void epilogue_row_tma(const TcParams& p, const CUtens
     }
   }
   if (!p.unpool_mask) {
-    if (tq == 0) tma_store_wait_read();
-    epi_bar();
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
 #pragma unroll
     for (int c16 = 0; c16 < 8; ++c16)  // 128-byte row, 16-byte chunk c16 lands at chunk (c16 ^ row%8): the SWIZZLE_128B pattern
-      *reinterpret_cast<uint4*>(stage + tq * 128 + ((c16 ^ (tq & 7)) << 4)) =
+      *reinterpret_cast<uint4*>(wstage + lane * 128 + ((c16 ^ (lane & 7)) << 4)) =
           make_uint4(packed[4 * c16], packed[4 * c16 + 1], packed[4 * c16 + 2], packed[4 * c16 + 3]);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    epi_bar();
-    if (tq == 0) tma_store_4d(map_o, stage, n0, x0, y, img);
+    __syncwarp();
+    if (lane == 0) tma_store_4d(map_o, wstage, n0, xw, y, img);
     return;
   }
-  // max-unpool: this input row feeds output rows 2y, 2y+1, 256 px wide = 2 x 128-px tiles each
+  // max-unpool: the warp's 32 input pixels feed 64 output pixels on each of rows 2y, 2y+1 = four 32-px stores
   const uint32_t mw[16] = {mrow[0].x, mrow[0].y, mrow[0].z, mrow[0].w, mrow[1].x, mrow[1].y, mrow[1].z, mrow[1].w,
                            mrow[2].x, mrow[2].y, mrow[2].z, mrow[2].w, mrow[3].x, mrow[3].y, mrow[3].z, mrow[3].w};
 #pragma unroll
   for (int round = 0; round < 4; ++round) {
     const int dh = round >> 1, half = round & 1;
-    if (tq == 0) tma_store_wait_read();
-    epi_bar();
-    if ((tq >> 6) == half) {
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+    if ((lane >> 4) == half) {
 #pragma unroll
       for (int dw = 0; dw < 2; ++dw) {
         const uint32_t pos = static_cast<uint32_t>(dh * 2 + dw);
-        const int row = 2 * (tq & 63) + dw;
+        const int row = 2 * (lane & 15) + dw;
 #pragma unroll
         for (int c16 = 0; c16 < 8; ++c16) {
           uint32_t sel[4];
@@ -424,13 +426,13 @@ __device__ __forceinline__ void epilogue_row_tma(const TcParams& p, const CUtens
             const uint32_t hi = (((mb >> 8) & 0xFFu) == pos) ? 0xFFFF0000u : 0u;
             sel[k] = packed[i] & (lo | hi);
           }
-          *reinterpret_cast<uint4*>(stage + row * 128 + ((c16 ^ (row & 7)) << 4)) = make_uint4(sel[0], sel[1], sel[2], sel[3]);
+          *reinterpret_cast<uint4*>(wstage + row * 128 + ((c16 ^ (row & 7)) << 4)) = make_uint4(sel[0], sel[1], sel[2], sel[3]);
         }
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    epi_bar();
-    if (tq == 0) tma_store_4d(map_o, stage, n0, 2 * x0 + half * 128, 2 * y + dh, img);
+    __syncwarp();
+    if (lane == 0) tma_store_4d(map_o, wstage, n0, 2 * xw + half * 32, 2 * y + dh, img);
   }
 }
 
@@ -677,7 +679,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
           const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
-          epilogue_row_tma(p, &map_o, stage, trow, s_cls, img, y_base + j * kRows + r, x0, q * 32 + lane, n0);
+          epilogue_row_tma(p, &map_o, stage + q * 4096, trow, s_cls, img, y_base + j * kRows + r, x0 + q * 32, lane, n0);
         }
       } else {
 #pragma unroll
@@ -691,7 +693,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       __syncwarp();
       if (lane == 0) mbar_arrive(t_empty + acc);
     }
-    if (p.epi_tma && q == 0 && lane == 0) tma_store_wait_read();  // the staging tile must outlive the last bulk store's read
+    if (p.epi_tma && lane == 0) tma_store_wait_read();  // each warp's staging slice must outlive its last bulk store's read
   }
   __syncthreads();
   if (warp == 2) {
@@ -882,7 +884,7 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
           const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + (3 - r)) * 64);
-          epilogue_row_tma(p, &map_o, stage, trow, s_cls, img, y_base + j * kRows + r, x0, q * 32 + lane, 0);
+          epilogue_row_tma(p, &map_o, stage + q * 4096, trow, s_cls, img, y_base + j * kRows + r, x0 + q * 32, lane, 0);
         }
       } else {
 #pragma unroll
@@ -896,7 +898,7 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(t_empty + acc);
     }
-    if (p.epi_tma && q == 0 && lane == 0) tma_store_wait_read();  // the staging tile must outlive the last bulk store's read
+    if (p.epi_tma && lane == 0) tma_store_wait_read();  // each warp's staging slice must outlive its last bulk store's read
   }
   __syncthreads();
   if (warp == 2) {
@@ -931,12 +933,12 @@ void encode(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const 
   if (r != CUDA_SUCCESS) fail(SIVO_ECUDA, "cuTensorMapEncodeTiled failed with %d", static_cast<int>(r));
 }
 
-// output tensor map of the TMA-store epilogue: NHWC tensor with `c` channels of `elem_bytes`, box = {box_c, 128 px, 1, 1}
+// output tensor map of the TMA-store epilogue: NHWC tensor with `c` channels, box = {box_c, 32 px, 1, 1}
 void encode_out(CUtensorMap* m, void* base, int c, int w, int h, int n, int box_c, bool f32) {
   const size_t eb = f32 ? 4 : 2;
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * eb, static_cast<cuuint64_t>(w) * c * eb, static_cast<cuuint64_t>(h) * w * c * eb};
-  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), 128, 1, 1};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), 32, 1, 1};  // one epilogue warp's 32-pixel span
   encode(m, base, 4, dims, strides, box, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
          f32 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B);
 }
