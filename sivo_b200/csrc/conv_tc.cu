@@ -22,7 +22,6 @@
 
 #include <algorithm>
 #include <cstdlib>
-#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -43,8 +42,7 @@ struct TcParams {
   int n_tile;              // UMMA N (16 for the float logits layer, else 64 or 128)
   int chunks;              // Cin / 64
   int w_rep;               // weight tensor replicas in global memory (spreads the L2 hot spot all CTAs hammer)
-  int epi_tma;             // 1: the epilogue stages each output row in shared memory and writes it with one TMA store
-  int dbg_noepi;           // timing experiment only: the epilogue releases the accumulators without reading them
+  int dbg_noepi;           // timing experiment only: 1 = epilogue does nothing, 2 = TMEM loads only, 3 = no global stores
   int dbg_noshift;         // timing experiment only: ignore the kw shift of the A operand (wrong results)
   int b_stages;            // weight ring depth (as many of kMaxBStages as fit in shared memory)
   int out_f32;             // 1: 16-channel float output (logits)
@@ -300,142 +298,6 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t trow, c
     }
 }
 
-// TMA-store epilogue (n_tile == 64).  Measured (profiles/r1_notes.md): with per-thread st.global.v4 -- one pixel per
-// lane, so every warp store touches 32 different 128-byte lines -- the stores alone cost 0.23 ms of a 1.37 ms frame
-// because the epilogue then outlasts the next block's MMAs.  Here the 128 epilogue threads write their pixel's 128 bytes
-// into a 16 KB swizzled staging tile (conflict-free st.shared) and one thread issues a single bulk tensor store per row;
-// rows / pixels outside the image are clipped by the TMA unit.  `tq` = pixel index inside the 128-px strip.
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-
-// Each epilogue warp owns a 4 KB slice of the staging tile (its 32 pixels x 128 B) and its own bulk-store stream, so the
-// four warps never wait for each other: lane 0 waits for the warp's previous store to have read the slice, the warp
-// fills it, lane 0 issues the next store.  `wstage` = this warp's slice, `xw` = first pixel of the warp's 32-px span.
-__device__ __forceinline__ void epilogue_row_tma(const TcParams& p, const CUtensorMap* map_o, uint8_t* wstage, uint32_t trow, const float* s_cls,
-                                                 int img, int y, int xw, int lane, int n0) {
-  if (y >= p.H) return;  // warp-uniform
-  const int x = xw + lane;
-  if (p.cls_w) {  // 1x1 classifier: 16 float logits per pixel, 64 B rows, no swizzle
-    float l[16];
-#pragma unroll
-    for (int jj = 0; jj < 16; ++jj) l[jj] = __ldg(p.cls_b + jj);
-    for (int cc = 0; cc < 64; cc += 32) {
-      uint32_t v[32];
-      tmem_ld32(trow + cc, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float t = __fadd_rn(__uint_as_float(v[i]), __ldg(p.bias + cc + i));
-        if (p.has_bn) t = __fadd_rn(__fmul_rn(t, __ldg(p.bn_scale + cc + i)), __ldg(p.bn_shift + cc + i));
-        if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
-        const float hv = __half2float(__float2half_rn(t));
-        const float4* w4 = reinterpret_cast<const float4*>(s_cls + (cc + i) * 16);
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const float4 w = w4[q4];
-          l[4 * q4] = fmaf(hv, w.x, l[4 * q4]);
-          l[4 * q4 + 1] = fmaf(hv, w.y, l[4 * q4 + 1]);
-          l[4 * q4 + 2] = fmaf(hv, w.z, l[4 * q4 + 2]);
-          l[4 * q4 + 3] = fmaf(hv, w.w, l[4 * q4 + 3]);
-        }
-      }
-    }
-    if (lane == 0) tma_store_wait_read();
-    __syncwarp();
-    float4* dst = reinterpret_cast<float4*>(wstage + lane * 64);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dst[i] = make_float4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    if (lane == 0) tma_store_4d(map_o, wstage, 0, xw, y, img);
-    return;
-  }
-  // 64 channels of this pixel as 32 half2 words: bias / BN / ReLU / (dropout)
-  uint32_t packed[32];
-  uint32_t bits[4] = {0, 0, 0, 0};
-  uint4 mrow[4] = {};
-  if (p.unpool_mask && x < p.W) {
-    const uint4* mp = reinterpret_cast<const uint4*>(p.unpool_mask + ((static_cast<size_t>(img % p.mask_n) * p.H + y) * p.W + x) * p.cout_total + n0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) mrow[i] = __ldg(mp + i);
-  }
-#pragma unroll
-  for (int cc = 0; cc < 64; cc += 32) {
-    uint32_t v[32];
-    tmem_ld32(trow + cc, v);
-    const int c0 = n0 + cc;
-    if (p.has_drop && ((c0 & 127) == 0 || cc == 0))
-      dropout_bits128(p.seed, *p.frame, p.drop_layer, img, static_cast<uint32_t>(y * p.W + x), c0 >> 7, bits);
-    const uint32_t keep = p.has_drop ? bits[(c0 >> 5) & 3] : 0xFFFFFFFFu;
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      float f[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int c = c0 + i + e;
-        float t = __fadd_rn(__uint_as_float(v[i + e]), __ldg(p.bias + c));
-        if (p.has_bn) t = __fadd_rn(__fmul_rn(t, __ldg(p.bn_scale + c)), __ldg(p.bn_shift + c));
-        if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
-        f[e] = t;
-      }
-      __half2 h = __floats2half2_rn(f[0], f[1]);
-      if (p.has_drop) {
-        __half2 sc = __floats2half2_rn((keep >> i) & 1u ? p.drop_scale : 0.f, (keep >> (i + 1)) & 1u ? p.drop_scale : 0.f);
-        h = __hmul2(h, sc);
-      }
-      packed[(cc >> 1) + (i >> 1)] = *reinterpret_cast<uint32_t*>(&h);
-    }
-  }
-  if (!p.unpool_mask) {
-    if (lane == 0) tma_store_wait_read();
-    __syncwarp();
-#pragma unroll
-    for (int c16 = 0; c16 < 8; ++c16)  // 128-byte row, 16-byte chunk c16 lands at chunk (c16 ^ row%8): the SWIZZLE_128B pattern
-      *reinterpret_cast<uint4*>(wstage + lane * 128 + ((c16 ^ (lane & 7)) << 4)) =
-          make_uint4(packed[4 * c16], packed[4 * c16 + 1], packed[4 * c16 + 2], packed[4 * c16 + 3]);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    if (lane == 0) tma_store_4d(map_o, wstage, n0, xw, y, img);
-    return;
-  }
-  // max-unpool: the warp's 32 input pixels feed 64 output pixels on each of rows 2y, 2y+1 = four 32-px stores
-  const uint32_t mw[16] = {mrow[0].x, mrow[0].y, mrow[0].z, mrow[0].w, mrow[1].x, mrow[1].y, mrow[1].z, mrow[1].w,
-                           mrow[2].x, mrow[2].y, mrow[2].z, mrow[2].w, mrow[3].x, mrow[3].y, mrow[3].z, mrow[3].w};
-#pragma unroll
-  for (int round = 0; round < 4; ++round) {
-    const int dh = round >> 1, half = round & 1;
-    if (lane == 0) tma_store_wait_read();
-    __syncwarp();
-    if ((lane >> 4) == half) {
-#pragma unroll
-      for (int dw = 0; dw < 2; ++dw) {
-        const uint32_t pos = static_cast<uint32_t>(dh * 2 + dw);
-        const int row = 2 * (lane & 15) + dw;
-#pragma unroll
-        for (int c16 = 0; c16 < 8; ++c16) {
-          uint32_t sel[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int i = 4 * c16 + k;  // half2 index: channels 2i, 2i+1 -> mask bytes 2i, 2i+1
-            const uint32_t mb = mw[i >> 1] >> ((i & 1) * 16);
-            const uint32_t lo = ((mb & 0xFFu) == pos) ? 0x0000FFFFu : 0u;
-            const uint32_t hi = (((mb >> 8) & 0xFFu) == pos) ? 0xFFFF0000u : 0u;
-            sel[k] = packed[i] & (lo | hi);
-          }
-          *reinterpret_cast<uint4*>(wstage + row * 128 + ((c16 ^ (row & 7)) << 4)) = make_uint4(sel[0], sel[1], sel[2], sel[3]);
-        }
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    if (lane == 0) tma_store_4d(map_o, wstage, n0, 2 * xw + half * 32, 2 * y + dh, img);
-  }
-}
-
 // Two vertically adjacent output rows (y even) with the pooling epilogue: bias / BN / ReLU -> half (the value the
 // unfused path would store) -> 2x2 max with first-maximum argmax; the horizontal neighbour lives in the adjacent lane.
 __device__ __forceinline__ void epilogue_pool_rows(const TcParams& p, uint32_t trow0, uint32_t trow1, int img, int y, int x, int n0, int lane) {
@@ -499,8 +361,7 @@ __device__ __forceinline__ void epilogue_pool_rows(const TcParams& p, uint32_t t
 //               the K*K taps and released; the ring double-buffers chunks.
 template <int K, bool ROLL, int kRows>
 __global__ void __launch_bounds__(kTcThreads, 1)
-k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-          const __grid_constant__ CUtensorMap map_o, const TcParams p) {
+k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   constexpr int RK = kRows + K - 1;                  // halo rows one row pair reads (per chunk)
   constexpr int kSlots = ROLL ? RK : 2 * RK;         // ROLL: rows are released as soon as their last tap row is issued
   constexpr int kPad = (K - 1) / 2;
@@ -511,8 +372,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   const int b_bytes = p.n_tile * 128;
   const int b_stride = (b_bytes + 1023) & ~1023;
   const int kBStages = p.b_stages;
-  uint8_t* stage = b_stages + kBStages * b_stride;  // 16 KB output staging tile of the TMA-store epilogue
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + (p.epi_tma ? 16384 : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_stages + kBStages * b_stride);
   uint64_t* a_full = bars;                       // [kSlots]
   uint64_t* a_empty = a_full + kSlots;           // [kSlots]
   uint64_t* b_full = a_empty + kSlots;           // [kBStages]
@@ -675,12 +535,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
           epilogue_pool_rows(p, trow, trow + p.n_tile, img, y_base + j * kRows + r, x, n0, lane);
         }
-      } else if (p.epi_tma) {
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-          const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
-          epilogue_row_tma(p, &map_o, stage + q * 4096, trow, s_cls, img, y_base + j * kRows + r, x0 + q * 32, lane, n0);
-        }
       } else {
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
@@ -693,7 +547,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       __syncwarp();
       if (lane == 0) mbar_arrive(t_empty + acc);
     }
-    if (p.epi_tma && lane == 0) tma_store_wait_read();  // each warp's staging slice must outlive its last bulk store's read
   }
   __syncthreads();
   if (warp == 2) {
@@ -712,8 +565,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // instructions.  Weights come as [kw][kh][cout][cin] so one TMA box of 128 rows lands both taps of a pair.
 template <int K>
 __global__ void __launch_bounds__(kTcThreads, 1)
-k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_o, const TcParams p) {
+k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   constexpr int kRows = 4, RK = kRows + K - 1, kSlots = RK, kPad = (K - 1) / 2, NP = (K + 1) / 2;
   constexpr int kBBytes = 128 * 128;  // two stacked 64 x 64 weight tiles
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -721,8 +573,7 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* a_slots = smem;
   uint8_t* b_stages = smem + kSlots * kSlotBytes;
   const int kBStages = p.b_stages;
-  uint8_t* stage = b_stages + kBStages * kBBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + (p.epi_tma ? 16384 : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_stages + kBStages * kBBytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kSlots;
   uint64_t* b_full = a_empty + kSlots;
@@ -880,12 +731,6 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + (3 - r)) * 64);
           epilogue_pool_rows(p, trow, trow - 64, img, y_base + j * kRows + r, x, 0, lane);
         }
-      } else if (p.epi_tma) {
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-          const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + (3 - r)) * 64);
-          epilogue_row_tma(p, &map_o, stage + q * 4096, trow, s_cls, img, y_base + j * kRows + r, x0 + q * 32, lane, 0);
-        }
       } else {
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
@@ -898,7 +743,6 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(t_empty + acc);
     }
-    if (p.epi_tma && lane == 0) tma_store_wait_read();  // each warp's staging slice must outlive its last bulk store's read
   }
   __syncthreads();
   if (warp == 2) {
@@ -925,28 +769,17 @@ EncodeFn encode_fn() {
   return fn;
 }
 
-void encode(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
-            CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B) {
+void encode(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
   cuuint32_t elem[5] = {1, 1, 1, 1, 1};
-  CUresult r = encode_fn()(m, dt, rank, base, dims, strides_bytes, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, base, dims, strides_bytes, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) fail(SIVO_ECUDA, "cuTensorMapEncodeTiled failed with %d", static_cast<int>(r));
-}
-
-// output tensor map of the TMA-store epilogue: NHWC tensor with `c` channels, box = {box_c, 32 px, 1, 1}
-void encode_out(CUtensorMap* m, void* base, int c, int w, int h, int n, int box_c, bool f32) {
-  const size_t eb = f32 ? 4 : 2;
-  cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
-  cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * eb, static_cast<cuuint64_t>(w) * c * eb, static_cast<cuuint64_t>(h) * w * c * eb};
-  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), 32, 1, 1};  // one epilogue warp's 32-pixel span
-  encode(m, base, 4, dims, strides, box, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
-         f32 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 }  // namespace
 
 struct ConvTcPlan {
-  CUtensorMap map_a, map_b, map_o;
+  CUtensorMap map_a, map_b;
   TcParams p;
   dim3 grid;
   size_t smem;
@@ -963,7 +796,7 @@ void conv_tc_dispatch(const ConvTcPlan& plan, cudaStream_t s, bool configure) {
     // the limit is per kernel function, not per launch: always raise it to the full 227 KB so that plans of different
     // sizes that share an instantiation (e.g. the 16-wide logits tile and a 64-wide layer) cannot lower it for each other
     if (configure) SIVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    else kern<<<plan.grid, kTcThreads, plan.smem, s>>>(plan.map_a, plan.map_b, plan.map_o, plan.p);
+    else kern<<<plan.grid, kTcThreads, plan.smem, s>>>(plan.map_a, plan.map_b, plan.p);
   };
   const int K = plan.k;
   if (plan.pair) { if (K == 7) go(k_conv_tc_pair<7>); else go(k_conv_tc_pair<3>); }
@@ -980,17 +813,16 @@ int tc_rows(int K, bool roll, int n_tile, int columns = 1 << 30, int H = 1 << 20
   if (!(roll && n_tile <= 64)) return 2;
   return static_cast<long>(columns) * ceil_div(H, 4) < 148 ? 2 : 4;
 }
-size_t tc_smem_bytes(int K, bool roll, int n_tile, int stages, bool epi_tma = false) {
+size_t tc_smem_bytes(int K, bool roll, int n_tile, int stages) {
   const int rows = tc_rows(K, roll, n_tile);  // the 4-row variant is the larger footprint
   const int rk = rows + K - 1;
   const int slots = roll ? rk : 2 * rk;
   const int b_stride = (n_tile * 128 + 1023) & ~1023;
-  return 1024 + static_cast<size_t>(slots) * kSlotBytes + static_cast<size_t>(stages) * b_stride + (2 * slots + 2 * stages + 4) * 8 + 16 + 64 * 16 * 4 +
-         (epi_tma ? 16384 : 0);  // barriers, TMEM slot, fused-classifier weights, output staging tile
+  return 1024 + static_cast<size_t>(slots) * kSlotBytes + static_cast<size_t>(stages) * b_stride + (2 * slots + 2 * stages + 4) * 8 + 16 + 64 * 16 * 4;  // barriers, TMEM slot, fused-classifier weights
 }
-int tc_stages(int K, bool roll, int n_tile, bool epi_tma = false) {  // deepest weight ring that fits (0 = configuration does not fit)
+int tc_stages(int K, bool roll, int n_tile) {  // deepest weight ring that fits (0 = configuration does not fit)
   for (int st = kMaxBStages; st >= 3; --st)
-    if (tc_smem_bytes(K, roll, n_tile, st, epi_tma) <= 227 * 1024) return st;
+    if (tc_smem_bytes(K, roll, n_tile, st) <= 227 * 1024) return st;
   return 0;
 }
 int tc_pick_n(const Op& op, const TensorView& out, bool roll) {
@@ -1074,21 +906,17 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   p.unpool_mask = nullptr; p.mask_n = 1;
   p.dbg_noshift = 0;
   p.dbg_noepi = 0;
-  if (const char* e = std::getenv("SIVO_B200_TC_NOEPI")) p.dbg_noepi = atoi(e);  // 1: nothing, 2: TMEM loads only, 3: no global stores
+  if (const char* e = std::getenv("SIVO_B200_TC_NOEPI")) p.dbg_noepi = atoi(e);
   if (const char* e = std::getenv("SIVO_B200_TC_NOSHIFT")) p.dbg_noshift = e[0] == '1';
   p.pool_out = nullptr; p.pool_mask = nullptr;
   p.cls_w = nullptr; p.cls_b = nullptr; p.cls_out = nullptr; p.cls_stride = 0;
   plan->grid = dim3(p.strips * ceil_div(total_pairs, ppc), cout_tiles, in.n);
-  const char* epi_env = std::getenv("SIVO_B200_TC_EPI_TMA");
-  p.epi_tma = (n_tile == 64 && !p.out_f32 && tc_stages(K, roll, n_tile, true) > 0 && !(epi_env && epi_env[0] == '0')) ? 1 : 0;
-  memset(&plan->map_o, 0, sizeof plan->map_o);
-  if (p.epi_tma) encode_out(&plan->map_o, out.p, out.cs, out.w, out.h, out.n, 64, false);
-  p.b_stages = tc_stages(K, roll, n_tile, p.epi_tma != 0);
+  p.b_stages = tc_stages(K, roll, n_tile);
   if (const char* e = std::getenv("SIVO_B200_TC_BSTAGES")) p.b_stages = std::max(2, std::min(p.b_stages, atoi(e)));  // experiment knob
-  plan->smem = tc_smem_bytes(K, roll, n_tile, p.b_stages, p.epi_tma != 0);
+  plan->smem = tc_smem_bytes(K, roll, n_tile, p.b_stages);
   const char* pair_env = std::getenv("SIVO_B200_TC_PAIR");
   if (roll && rows == 4 && n_tile == 64 && op.cout_p == 64 && !p.out_f32 && (K == 7 || K == 3) && op.w_tc_pair.p &&
-      pair_env && pair_env[0] == '1') {  // opt-in: measured equal to the N = 64 kernel on B200 (profiles/r1_notes.md)
+      !(pair_env && pair_env[0] == '0')) {  // default on: ~2 % faster than the N = 64 kernel (profiles/r1_notes.md)
     // paired-tap kernel: weights as one [K*K*64 rows][64 cin] matrix in (kw, kh, cout) row order, 128-row boxes
     const size_t one = static_cast<size_t>(K) * K * 64 * 128;
     void* wbase = op.w_tc_pair.p;
@@ -1105,7 +933,7 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
     plan->pair = true;
     const int slots = rows + K - 1;
     int st = 6;
-    auto bytes = [&](int n) { return 1024 + static_cast<size_t>(slots) * kSlotBytes + static_cast<size_t>(n) * 16384 + (2 * slots + 2 * n + 4) * 8 + 16 + 64 * 16 * 4 + (p.epi_tma ? 16384 : 0); };
+    auto bytes = [&](int n) { return 1024 + static_cast<size_t>(slots) * kSlotBytes + static_cast<size_t>(n) * 16384 + (2 * slots + 2 * n + 4) * 8 + 16 + 64 * 16 * 4; };
     while (st > 2 && bytes(st) > 227 * 1024) --st;
     p.b_stages = st;
     plan->smem = bytes(st);
@@ -1130,7 +958,6 @@ void conv_tc_set_unpool(ConvTcPlan& plan, const uint8_t* mask, int mask_n, void*
   plan.p.unpool_mask = mask;
   plan.p.mask_n = mask_n;
   plan.p.out = out_2h_2w;
-  if (plan.p.epi_tma) encode_out(&plan.map_o, out_2h_2w, plan.p.cout_total, 2 * plan.p.W, 2 * plan.p.H, plan.p.N_batch, 64, false);
 }
 
 std::vector<__half> conv_tc_pair_weights(const float* w_cout_cin_k_k, int K) {
@@ -1152,7 +979,6 @@ bool conv_tc_can_fuse_pool(const ConvTcPlan& plan) {
 void conv_tc_set_pool(ConvTcPlan& plan, void* pooled, uint8_t* mask) {
   plan.p.pool_out = static_cast<__half*>(pooled);
   plan.p.pool_mask = mask;
-  plan.p.epi_tma = 0;  // the pooling epilogue writes its (4x smaller) outputs directly
 }
 
 bool conv_tc_can_fuse_classifier(const ConvTcPlan& plan) {
@@ -1164,7 +990,6 @@ void conv_tc_set_classifier(ConvTcPlan& plan, const float* w_cin_by_cout, int st
   plan.p.cls_stride = stride;
   plan.p.cls_b = bias;
   plan.p.cls_out = logits;
-  if (plan.p.epi_tma) encode_out(&plan.map_o, logits, 16, plan.p.W, plan.p.H, plan.p.N_batch, 16, true);
 }
 
 void conv_tc_launch(const ConvTcPlan& plan, const Op& op, cudaStream_t s) {
