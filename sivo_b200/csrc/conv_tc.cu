@@ -32,7 +32,8 @@ namespace sivo {
 
 namespace {
 
-constexpr int kTcThreads = 8 * 32;  // warps: 0 halo TMA, 1 weight TMA, 2-3 MMA issuers, 4-7 epilogue
+constexpr int kTcThreads = 12 * 32;  // warps: 0 halo TMA, 1 weight TMA, 2-3 MMA issuers, 4-11 epilogue (two per TMEM lane quarter)
+constexpr int kEpiWarps = 8;
 constexpr int kSlotBytes = 17 * 1024;  // one halo row: (128 + K - 1) px * 128 B, padded to a 1024-B multiple
 constexpr int kMaxBStages = 6;
 
@@ -99,7 +100,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
-    if (spin > (1u << 26)) __trap();
+    if (spin > (1u << 26)) asm volatile("trap;");  // inline: a __trap() call stub pins the whole kernel to the setmaxnreg minimum
   }
 }
 
@@ -400,7 +401,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     // two MMA issuer warps (each owns half of the output rows): every consumer-side release needs both commits
     for (int i = 0; i < kSlots; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 2); }
     for (int i = 0; i < kBStages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 2); }
-    for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 2); mbar_init(t_empty + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 2); mbar_init(t_empty + i, kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -415,6 +416,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
+  // 384 threads start with 168 registers each; the TMA / MMA-issue warpgroup needs few, the two epilogue warpgroups
+  // (32 accumulator words + packed outputs + masks per thread) need many: 128 x 56 + 256 x 216 = 62 464 <= 65 536
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
   if (warp == 0) {
     // ===== halo-row producer =====
     if (lane == 0) {
@@ -521,23 +526,31 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       if (elect_one()) umma_commit(t_full + acc);
       __syncwarp();
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
     // ===== epilogue: TMEM -> registers -> bias / BN / ReLU / dropout -> half (or float logits) -> global =====
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // Measured (profiles/r1_notes.md): with four epilogue warps the stores + arithmetic of block j outlast the MMAs of
+    // block j+1 (30 % of the frame's conv time).  Eight warps -- warps w and w+4 share a TMEM lane quarter and split the
+    // rows of a block between them -- halve the epilogue's duration so it fits under the MMAs again.
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int eset = (warp - 4) >> 2;  // 0: first half of the block's rows, 1: second half
     const int x = x0 + q * 32 + lane;
     for (int j = 0; j < npairs; ++j) {
       const int acc = j & 1;
       mbar_wait(t_full + acc, (j >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      constexpr int kPer = kRows / 2;  // rows per epilogue set
       if (p.pool_out) {
-#pragma unroll
-        for (int r = 0; r < kRows; r += 2) {
+        if (kRows == 4 || eset == 0) {  // a row pair per set (kRows == 2: one pair, taken by set 0)
+          const int r = kRows == 4 ? 2 * eset : 0;
           const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
           epilogue_pool_rows(p, trow, trow + p.n_tile, img, y_base + j * kRows + r, x, n0, lane);
         }
       } else {
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) {
+        for (int rr = 0; rr < kPer; ++rr) {
+          const int r = eset * kPer + rr;
           const int y = y_base + j * kRows + r;
           const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
           epilogue_row(p, trow, s_cls, img, y, x, n0);
@@ -597,7 +610,7 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int i = 0; i < kSlots; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
     for (int i = 0; i < kBStages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -612,6 +625,8 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
   if (warp == 0) {
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
@@ -718,22 +733,24 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       __syncwarp();
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
     const int q = warp & 3;
+    const int eset = (warp - 4) >> 2;  // two warps per TMEM lane quarter: rows {0,1} and {2,3}
     const int x = x0 + q * 32 + lane;
     for (int j = 0; j < npairs; ++j) {
       const int acc = j & 1;
       mbar_wait(t_full + acc, (j >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (p.pool_out) {
-#pragma unroll
-        for (int r = 0; r < kRows; r += 2) {  // accumulators sit in decreasing row order: row r+1 is 64 columns below row r
-          const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + (3 - r)) * 64);
-          epilogue_pool_rows(p, trow, trow - 64, img, y_base + j * kRows + r, x, 0, lane);
-        }
+      if (p.pool_out) {  // accumulators sit in decreasing row order: row r+1 is 64 columns below row r
+        const int r = 2 * eset;
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + (3 - r)) * 64);
+        epilogue_pool_rows(p, trow, trow - 64, img, y_base + j * kRows + r, x, 0, lane);
       } else {
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) {
+        for (int rr = 0; rr < 2; ++rr) {
+          const int r = 2 * eset + rr;
           const int y = y_base + j * kRows + r;
           const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + (3 - r)) * 64);
           epilogue_row(p, trow, s_cls, img, y, x, 0);
