@@ -271,15 +271,18 @@ def main():
     def host_step(i):
         j = i % n_frames
         left, gl, gr = h_fr[j]
-        res = seg.segmentImage(left, out=out_np)  # host image in, host maps out (H2D + D2H inside)
+        # the three operator calls of a frame are independent (the reference runs the two extractors on two threads,
+        # src/orbslam/Frame.cc:126-129); each call is synchronous for its caller: host image in, host results out, copies inside
         out = [None, None]
 
-        def right():
-            out[1] = orb_r(gr, None, want_pyramid=True, pyramid_buffers=pyr_np[1])
-        t = threading.Thread(target=right)
-        t.start()
-        out[0] = orb_l(gl, None, want_pyramid=True, pyramid_buffers=pyr_np[0])
-        t.join()
+        def orb_call(k, extractor, gray):
+            out[k] = extractor(gray, None, want_pyramid=True, pyramid_buffers=pyr_np[k])
+        ts = [threading.Thread(target=orb_call, args=(0, orb_l, gl)), threading.Thread(target=orb_call, args=(1, orb_r, gr))]
+        for t in ts:
+            t.start()
+        res = seg.segmentImage(left, out=out_np)
+        for t in ts:
+            t.join()
         return res, out
 
     def barrier():

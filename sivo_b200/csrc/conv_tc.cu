@@ -360,12 +360,14 @@ __device__ __forceinline__ void epilogue_pool_rows(const TcParams& p, uint32_t t
 //               strip, so each input row is fetched once per CTA.
 // ROLL = false: Cin = 64 * NC; per (row pair, chunk) the kRows+K-1 halo rows of that chunk are fetched, used by
 //               the K*K taps and released; the ring double-buffers chunks.
-template <int K, bool ROLL, int kRows>
+// KW < K : the kernel is K x KW over a *window-folded* input (KW = 1: every pixel's 64 "channels" are the 8-pixel x
+//               8-channel window starting at it, so a 3-channel K x K layer is a K x 1 layer; see conv_tc_plan).
+template <int K, bool ROLL, int kRows, int KW = K>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   constexpr int RK = kRows + K - 1;                  // halo rows one row pair reads (per chunk)
   constexpr int kSlots = ROLL ? RK : 2 * RK;         // ROLL: rows are released as soon as their last tap row is issued
-  constexpr int kPad = (K - 1) / 2;
+  constexpr int kPad = (K - 1) / 2, kPadW = (KW - 1) / 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_slots = smem;
@@ -436,8 +438,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           yy = y_base + j * kRows - kPad + rem % RK;
         }
         mbar_wait(a_empty + slot, (round & 1) ^ 1);
-        mbar_expect_tx(a_full + slot, static_cast<uint32_t>((128 + K - 1) * 128));
-        tma_load_4d(a_slots + slot * kSlotBytes, &map_a, a_full + slot, ch * 64, x0 - kPad, yy, img);
+        mbar_expect_tx(a_full + slot, static_cast<uint32_t>((128 + KW - 1) * 128));
+        tma_load_4d(a_slots + slot * kSlotBytes, &map_a, a_full + slot, ch * 64, x0 - kPadW, yy, img);
       }
     }
   } else if (warp == 1) {
@@ -448,11 +450,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       uint32_t it = 0;
       for (int j = 0; j < npairs; ++j)
         for (int ch = 0; ch < NC; ++ch)
-          for (int tap = 0; tap < K * K; ++tap, ++it) {
+          for (int tap = 0; tap < K * KW; ++tap, ++it) {
             const int st = it % kBStages;
             mbar_wait(b_empty + st, ((it / kBStages) & 1) ^ 1);
             mbar_expect_tx(b_full + st, static_cast<uint32_t>(b_bytes));
-            tma_load_3d(b_stages + st * b_stride, &map_b, b_full + st, ch * 64, n0, tap + w_replica * K * K);
+            tma_load_3d(b_stages + st * b_stride, &map_b, b_full + st, ch * 64, n0, tap + w_replica * K * KW);
           }
     }
   } else if (warp == 2 || warp == 3) {
@@ -489,7 +491,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           const uint32_t first_row = (ch | kh) ? 1u : 0u;
           const uint32_t kw_step = p.dbg_noshift ? 0u : 8u;
 #pragma unroll
-          for (int kw = 0; kw < K; ++kw) {
+          for (int kw = 0; kw < KW; ++kw) {
             mbar_wait(b_full + st, b_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // descriptors: the high word is constant; the low word is (address >> 4) | LBO; a K step of 16 halfs
@@ -801,6 +803,7 @@ struct ConvTcPlan {
   dim3 grid;
   size_t smem;
   int k, rows;
+  int kw;             // filter width the kernel walks (== k, or 1 for a window-folded layer)
   bool roll;
   bool pair = false;  // paired-tap kernel (64 -> 64 channels, 4-row blocks)
   DevBuf w_replicas;  // private replicated copy of the weights (w_rep > 1)
@@ -817,6 +820,11 @@ void conv_tc_dispatch(const ConvTcPlan& plan, cudaStream_t s, bool configure) {
   };
   const int K = plan.k;
   if (plan.pair) { if (K == 7) go(k_conv_tc_pair<7>); else go(k_conv_tc_pair<3>); }
+  else if (plan.kw == 1 && K > 1) {  // window-folded first layer (K x 1)
+    if (!plan.roll) fail(SIVO_EINVAL, "window-folded convolution needs the rolling kernel");
+    if (plan.rows == 4) { if (K == 7) go(k_conv_tc<7, true, 4, 1>); else go(k_conv_tc<3, true, 4, 1>); }
+    else { if (K == 7) go(k_conv_tc<7, true, 2, 1>); else go(k_conv_tc<3, true, 2, 1>); }
+  }
   else if (plan.roll && plan.rows == 4) { if (K == 7) go(k_conv_tc<7, true, 4>); else if (K == 3) go(k_conv_tc<3, true, 4>); else go(k_conv_tc<1, true, 4>); }
   else if (plan.roll) { if (K == 7) go(k_conv_tc<7, true, 2>); else if (K == 3) go(k_conv_tc<3, true, 2>); else go(k_conv_tc<1, true, 2>); }
   else { if (K == 3) go(k_conv_tc<3, false, 2>); else go(k_conv_tc<1, false, 2>); }
@@ -854,6 +862,10 @@ bool conv_tc_supported(const Op& op, const TensorView& in, const TensorView& out
   if (const char* e = std::getenv("SIVO_B200_NO_TC")) if (e[0] == '1') return false;
   if (in.dt != DType::F16) return false;
   if (op.k != 1 && op.k != 3 && op.k != 7) return false;
+  if (op.fold_kw) {
+    if (in.cs != 8 || op.cin_p != 64 || (op.k != 3 && op.k != 7) || out.dt != DType::F16 || op.cout % 64 || out.cs != op.cout) return false;
+    return tc_stages(op.k, true, tc_pick_n(op, out, true)) > 0;
+  }
   if (in.cs % 64 || op.cin != in.cs) return false;
   if (out.dt == DType::F16) {
     if (op.cout % 64 || out.cs != op.cout) return false;
@@ -867,8 +879,20 @@ bool conv_tc_supported(const Op& op, const TensorView& in, const TensorView& out
 std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, const TensorView& out, const void* w_tc) {
   auto plan = std::make_shared<ConvTcPlan>();
   const int K = op.k;
-  const bool roll = in.cs == 64;
-  {  // input: NHWC half, dims (C, W, H, N)
+  const int KW = op.fold_kw ? 1 : K;
+  const bool roll = in.cs == 64 || op.fold_kw;
+  if (op.fold_kw) {
+    // window-folded input: `in` is the zero-padded 8-channel image [N][H][W + 8][8] half (3 zero pixels left, 5 right);
+    // "pixel" x of the operand is the 128-byte window of 8 pixels x 8 channels starting at padded pixel x, i.e. image
+    // pixels x-3 .. x+4: a tensor whose W stride (16 B) is smaller than its row (128 B).  TMA only needs 16-byte
+    // multiples, so one box {64, 128, 1, 1} lands the K = kw*8 + c operand rows of 128 output pixels, and the K x K
+    // layer over 3 channels becomes a K x 1 layer over these 64 -- no expanded tensor in HBM.  `in.w` counts the padded row.
+    const int w_valid = in.w - 8;
+    cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(w_valid), static_cast<cuuint64_t>(in.h), static_cast<cuuint64_t>(in.n)};
+    cuuint64_t strides[3] = {16, static_cast<cuuint64_t>(in.w) * 16, static_cast<cuuint64_t>(in.h) * in.w * 16};
+    cuuint32_t box[4] = {64, 128, 1, 1};
+    encode(&plan->map_a, in.p, 4, dims, strides, box);
+  } else {  // input: NHWC half, dims (C, W, H, N)
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(in.cs), static_cast<cuuint64_t>(in.w), static_cast<cuuint64_t>(in.h),
                           static_cast<cuuint64_t>(in.n)};
     cuuint64_t strides[3] = {static_cast<cuuint64_t>(in.cs) * 2, static_cast<cuuint64_t>(in.w) * in.cs * 2,
@@ -880,7 +904,7 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   int w_rep = 1;
   if (const char* e = std::getenv("SIVO_B200_TC_WREP")) w_rep = std::max(1, std::min(16, atoi(e)));
   {  // weights: [replica][tap][cout_p][cin_p] half, dims (cin, cout, replica * tap)
-    const size_t one = static_cast<size_t>(K) * K * op.cout_p * op.cin_p * 2;
+    const size_t one = static_cast<size_t>(K) * KW * op.cout_p * op.cin_p * 2;
     void* wbase = const_cast<void*>(w_tc);
     if (w_rep > 1) {
       plan->w_replicas.alloc(one * w_rep);
@@ -888,19 +912,19 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
         SIVO_CUDA(cudaMemcpy(plan->w_replicas.as<uint8_t>() + r * one, w_tc, one, cudaMemcpyDeviceToDevice));
       wbase = plan->w_replicas.p;
     }
-    cuuint64_t dims[3] = {static_cast<cuuint64_t>(op.cin_p), static_cast<cuuint64_t>(op.cout_p), static_cast<cuuint64_t>(K * K * w_rep)};
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(op.cin_p), static_cast<cuuint64_t>(op.cout_p), static_cast<cuuint64_t>(K * KW * w_rep)};
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(op.cin_p) * 2, static_cast<cuuint64_t>(op.cout_p) * op.cin_p * 2};
     cuuint32_t box[3] = {64, static_cast<cuuint32_t>(n_tile), 1};
     encode(&plan->map_b, wbase, 3, dims, strides, box);
   }
   TcParams& p = plan->p;
-  p.H = in.h; p.W = in.w; p.N_batch = in.n;
+  p.H = in.h; p.W = op.fold_kw ? in.w - 8 : in.w; p.N_batch = in.n;
   p.cout_total = out.cs;
   p.n_tile = n_tile;
-  p.chunks = in.cs / 64;
+  p.chunks = op.fold_kw ? 1 : in.cs / 64;
   p.w_rep = w_rep;
   p.out_f32 = out.dt == DType::F32;
-  p.strips = ceil_div(in.w, 128);
+  p.strips = ceil_div(p.W, 128);
   const int cout_tiles = p.out_f32 ? 1 : op.cout_p / n_tile;
   const int columns = p.strips * in.n * cout_tiles;
   const int rows = tc_rows(K, roll, n_tile, columns, in.h);
@@ -932,7 +956,7 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   if (const char* e = std::getenv("SIVO_B200_TC_BSTAGES")) p.b_stages = std::max(2, std::min(p.b_stages, atoi(e)));  // experiment knob
   plan->smem = tc_smem_bytes(K, roll, n_tile, p.b_stages);
   const char* pair_env = std::getenv("SIVO_B200_TC_PAIR");
-  if (roll && rows == 4 && n_tile == 64 && op.cout_p == 64 && !p.out_f32 && (K == 7 || K == 3) && op.w_tc_pair.p &&
+  if (roll && !op.fold_kw && rows == 4 && n_tile == 64 && op.cout_p == 64 && !p.out_f32 && (K == 7 || K == 3) && op.w_tc_pair.p &&
       !(pair_env && pair_env[0] == '0')) {  // default on: ~2 % faster than the N = 64 kernel (profiles/r1_notes.md)
     // paired-tap kernel: weights as one [K*K*64 rows][64 cin] matrix in (kw, kh, cout) row order, 128-row boxes
     const size_t one = static_cast<size_t>(K) * K * 64 * 128;
@@ -956,6 +980,7 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
     plan->smem = bytes(st);
   }
   plan->k = K;
+  plan->kw = KW;
   plan->roll = roll;
   plan->rows = rows;
   if (!roll && K == 7) fail(SIVO_EINVAL, "7x7 with Cin > 64 is not built");

@@ -97,7 +97,8 @@ class Orb {
   PinnedBuf h_gray_, h_cand_, h_level_off_, h_sel_, h_angles_, h_desc_, h_pyr_;
   size_t pyr_bytes_ = 0, flat_bytes_ = 0;
   int cand_cap_ = 0, sel_cap_ = 0;
-  std::vector<std::vector<int>> last_cand_;  // per level: x, y, resp triples (test hook)
+  std::vector<uint32_t> last_cand_;  // last call's packed candidates (x | y << 12 | resp << 24), all levels (test hook)
+  std::vector<int> last_off_;        // per-level offsets into last_cand_
 };
 
 }  // namespace sivo

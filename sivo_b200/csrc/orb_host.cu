@@ -56,7 +56,7 @@ OrbTables orb_make_tables(int nfeatures, float scale_factor, int nlevels) {
 namespace {
 struct QNode {
   int ulx, uly, urx, bry;
-  std::vector<int> keys;
+  int begin = 0, count = 0;  // this node's keys: perm[begin, begin + count), in the reference's vKeys order
   bool no_more = false;
   int prev = -1, next = -1;  // intrusive list links (arena indices)
   int seq = 0;               // creation order among splittable nodes: the documented tie-break
@@ -90,16 +90,27 @@ struct QList {
 };
 }  // namespace
 
+// Keys live in one permutation array; a node owns a contiguous range of it and a split is a stable 4-way partition of
+// that range (children keep the parent's key order, as the reference's per-child push_back does), so the tree allocates
+// nothing per node.
 std::vector<int> orb_distribute(const float* xs, const float* ys, const float* resp, int n, int min_x, int max_x, int min_y,
                                 int max_y, int n_target) {
   std::vector<int> result;
   if (n <= 0) return result;
-  QList L;
+  static thread_local QList L;
+  static thread_local std::vector<int> perm, scratch, ini, pending, round;
+  static thread_local std::vector<uint8_t> quad;
+  L.arena.clear();
+  L.head = L.tail = -1;
+  L.size = 0;
   L.arena.reserve(static_cast<size_t>(n) * 4 + 64);
+  perm.resize(n);
+  scratch.resize(n);
+  quad.resize(n);
   int n_ini = static_cast<int>(std::round(static_cast<float>(max_x - min_x) / (max_y - min_y)));
   if (n_ini < 1) n_ini = 1;  // the reference divides by zero here for tall images; not reachable on this path
   const float hx = static_cast<float>(max_x - min_x) / n_ini;
-  std::vector<int> ini(n_ini);
+  ini.assign(n_ini, 0);
   for (int i = 0; i < n_ini; ++i) {
     int id = L.make();
     QNode& nd = L.arena[id];
@@ -110,50 +121,64 @@ std::vector<int> orb_distribute(const float* xs, const float* ys, const float* r
     L.push_back(id);
     ini[i] = id;
   }
+  // stable counting sort of the keys by initial cell
   for (int k = 0; k < n; ++k) {
     int cell = static_cast<int>(xs[k] / hx);
     if (cell >= n_ini) cell = n_ini - 1;
-    L.arena[ini[cell]].keys.push_back(k);
+    scratch[k] = cell;
+    ++L.arena[ini[cell]].count;
+  }
+  for (int i = 0, off = 0; i < n_ini; ++i) {
+    QNode& nd = L.arena[ini[i]];
+    nd.begin = off;
+    off += nd.count;
+    nd.count = 0;
+  }
+  for (int k = 0; k < n; ++k) {
+    QNode& nd = L.arena[ini[scratch[k]]];
+    perm[nd.begin + nd.count++] = k;
   }
   for (int i = L.head; i >= 0;) {
     QNode& nd = L.arena[i];
-    if (nd.keys.size() == 1) { nd.no_more = true; i = nd.next; }
-    else if (nd.keys.empty()) i = L.erase(i);
+    if (nd.count == 1) { nd.no_more = true; i = nd.next; }
+    else if (nd.count == 0) i = L.erase(i);
     else i = nd.next;
   }
   int seq = 0;
-  std::vector<int> pending;  // splittable children created in the current round
+  pending.clear();  // splittable children created in the current round
   auto split = [&](int id, int& n_expand) {
     // ExtractorNode::DivideNode (:488-542)
-    const int ulx = L.arena[id].ulx, uly = L.arena[id].uly, urx = L.arena[id].urx, bry = L.arena[id].bry;
-    const int half_x = static_cast<int>(std::ceil(static_cast<float>(urx - ulx) / 2));
-    const int half_y = static_cast<int>(std::ceil(static_cast<float>(bry - uly) / 2));
-    const int mx = ulx + half_x, my = uly + half_y;
-    int c[4];
-    for (int q = 0; q < 4; ++q) c[q] = L.make();
-    auto set = [&](int q, int a, int b, int cc, int d) {
-      QNode& nd = L.arena[c[q]];
-      nd.ulx = a; nd.uly = b; nd.urx = cc; nd.bry = d;
-    };
-    set(0, ulx, uly, mx, my);
-    set(1, mx, uly, urx, my);
-    set(2, ulx, my, mx, bry);
-    set(3, mx, my, urx, bry);
-    const std::vector<int> keys = L.arena[id].keys;  // copy: the arena may reallocate below
-    for (int k : keys) {
-      int q = xs[k] < mx ? (ys[k] < my ? 0 : 2) : (ys[k] < my ? 1 : 3);
-      L.arena[c[q]].keys.push_back(k);
+    const QNode parent = L.arena[id];  // copy: the arena may reallocate below
+    const int half_x = static_cast<int>(std::ceil(static_cast<float>(parent.urx - parent.ulx) / 2));
+    const int half_y = static_cast<int>(std::ceil(static_cast<float>(parent.bry - parent.uly) / 2));
+    const int mx = parent.ulx + half_x, my = parent.uly + half_y;
+    int cnt[4] = {0, 0, 0, 0};
+    int* keys = perm.data() + parent.begin;
+    for (int i = 0; i < parent.count; ++i) {
+      const int k = keys[i];
+      const int q = static_cast<int>(!(xs[k] < mx)) + 2 * static_cast<int>(!(ys[k] < my));  // UL, UR, BL, BR; branch-free
+      quad[i] = static_cast<uint8_t>(q);
+      ++cnt[q];
     }
+    int off[4] = {0, cnt[0], cnt[0] + cnt[1], cnt[0] + cnt[1] + cnt[2]};
+    const int start[4] = {off[0], off[1], off[2], off[3]};
+    for (int i = 0; i < parent.count; ++i) scratch[off[quad[i]]++] = keys[i];
+    std::copy(scratch.begin(), scratch.begin() + parent.count, keys);
+    const int bx[4][4] = {{parent.ulx, parent.uly, mx, my}, {mx, parent.uly, parent.urx, my},
+                          {parent.ulx, my, mx, parent.bry}, {mx, my, parent.urx, parent.bry}};
     for (int q = 0; q < 4; ++q) {
-      QNode& nd = L.arena[c[q]];
-      if (nd.keys.size() == 1) nd.no_more = true;
-      if (!nd.keys.empty()) {
-        L.push_front(c[q]);
-        if (nd.keys.size() > 1) {
-          ++n_expand;
-          nd.seq = ++seq;
-          pending.push_back(c[q]);
-        }
+      if (!cnt[q]) continue;  // empty children never enter the list
+      const int c = L.make();
+      QNode& nd = L.arena[c];
+      nd.ulx = bx[q][0]; nd.uly = bx[q][1]; nd.urx = bx[q][2]; nd.bry = bx[q][3];
+      nd.begin = parent.begin + start[q];
+      nd.count = cnt[q];
+      nd.no_more = cnt[q] == 1;
+      L.push_front(c);
+      if (cnt[q] > 1) {
+        ++n_expand;
+        nd.seq = ++seq;
+        pending.push_back(c);
       }
     }
   };
@@ -172,11 +197,11 @@ std::vector<int> orb_distribute(const float* xs, const float* ys, const float* r
     } else if (L.size + n_expand * 3 > n_target) {
       while (!finish) {
         const int prev = L.size;
-        std::vector<int> round = pending;
+        round = pending;
         pending.clear();
         // std::sort on (size, ExtractorNode*) in the reference (:671-676); ties by creation order here
         std::sort(round.begin(), round.end(), [&](int a, int b) {
-          size_t sa = L.arena[a].keys.size(), sb = L.arena[b].keys.size();
+          const int sa = L.arena[a].count, sb = L.arena[b].count;
           return sa != sb ? sa < sb : L.arena[a].seq < L.arena[b].seq;
         });
         for (int j = static_cast<int>(round.size()) - 1; j >= 0; --j) {
@@ -191,9 +216,9 @@ std::vector<int> orb_distribute(const float* xs, const float* ys, const float* r
   }
   result.reserve(L.size);
   for (int i = L.head; i >= 0; i = L.arena[i].next) {
-    const std::vector<int>& keys = L.arena[i].keys;
+    const int* keys = perm.data() + L.arena[i].begin;
     int best = keys[0];
-    for (size_t k = 1; k < keys.size(); ++k)
+    for (int k = 1; k < L.arena[i].count; ++k)
       if (resp[keys[k]] > resp[best]) best = keys[k];
     result.push_back(best);
   }
@@ -215,7 +240,13 @@ Orb::Orb(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th,
   tab_ = orb_make_tables(nfeatures, scale_factor, nlevels);
   SIVO_CUDA(cudaSetDevice(device_));
   std::call_once(g_pattern_once[device_ & 63], [] { orb_upload_pattern(); });
-  SIVO_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  {
+    // the extractor's kernels are tiny and its caller waits on them twice per image; give them the highest priority so
+    // they slot in ahead of the next wave of a long convolution kernel running on the same GPU
+    int lo = 0, hi = 0;
+    SIVO_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    SIVO_CUDA(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, hi));
+  }
   for (auto& e : ev_) SIVO_CUDA(cudaEventCreate(&e));
   d_umax_.alloc(sizeof(tab_.umax));
   SIVO_CUDA(cudaMemcpy(d_umax_.p, tab_.umax, sizeof(tab_.umax), cudaMemcpyHostToDevice));
@@ -368,21 +399,18 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
   std::vector<sivo_keypoint> out;
   out.reserve(nfeatures_ + 4 * nlevels_);
   OrbSelected* sel = h_sel_.as<OrbSelected>();
-  last_cand_.assign(nlevels_, {});
+  last_off_.assign(loff, loff + nlevels_ + 1);
+  last_cand_.assign(cand, cand + loff[nlevels_]);
   std::vector<float> xs, ys, rs;
   for (int l = 0; l < nlevels_; ++l) {
     const OrbLevel& lv = lt_.lv[l];
     const int b = loff[l], e = loff[l + 1], m = e - b;
     xs.resize(m); ys.resize(m); rs.resize(m);
-    last_cand_[l].resize(static_cast<size_t>(m) * 3);
     for (int i = 0; i < m; ++i) {
       uint32_t c = cand[b + i];
       xs[i] = static_cast<float>(c & 0xFFF);
       ys[i] = static_cast<float>((c >> 12) & 0xFFF);
       rs[i] = static_cast<float>(c >> 24);
-      last_cand_[l][3 * i] = c & 0xFFF;
-      last_cand_[l][3 * i + 1] = (c >> 12) & 0xFFF;
-      last_cand_[l][3 * i + 2] = c >> 24;
     }
     const int min_b = kEdge - 3;
     std::vector<int> keep = orb_distribute(xs.data(), ys.data(), rs.data(), m, min_b, lv.w - kEdge + 3, min_b, lv.h - kEdge + 3,
@@ -448,15 +476,15 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
 }
 
 void Orb::candidates(int level, int* xs, int* ys, int* resp, int cap, int* n) const {
-  if (level < 0 || level >= static_cast<int>(last_cand_.size())) fail(SIVO_EINVAL, "no candidates for level %d", level);
-  const auto& v = last_cand_[level];
-  int m = static_cast<int>(v.size() / 3);
+  if (level < 0 || level + 1 >= static_cast<int>(last_off_.size())) fail(SIVO_EINVAL, "no candidates for level %d", level);
+  const uint32_t* v = last_cand_.data() + last_off_[level];
+  const int m = last_off_[level + 1] - last_off_[level];
   if (n) *n = m;
   if (m > cap) fail(SIVO_ERANGE, "level %d has %d candidates, buffer holds %d", level, m, cap);
   for (int i = 0; i < m; ++i) {
-    if (xs) xs[i] = v[3 * i];
-    if (ys) ys[i] = v[3 * i + 1];
-    if (resp) resp[i] = v[3 * i + 2];
+    if (xs) xs[i] = static_cast<int>(v[i] & 0xFFF);
+    if (ys) ys[i] = static_cast<int>((v[i] >> 12) & 0xFFF);
+    if (resp) resp[i] = static_cast<int>(v[i] >> 24);
   }
 }
 

@@ -32,10 +32,13 @@ int SegNet::add_tensor(const std::string& name, int n, int c, int h, int w, int 
 
 void SegNet::prepare_conv(Op& op, const std::vector<Blob>& cb, const std::vector<Blob>* bn) {
   // K is the layer's kernel size; a tap-expanded layer (expand_k > 0) stores it as one tap over expand_k*blk channels
-  const int K = op.expand_k ? op.expand_k : op.k, cin = op.expand_k ? 3 : op.cin, cout = op.cout;
-  const int taps = op.expand_k ? 1 : K * K;
+  const int K = op.expand_k ? op.expand_k : op.k, cin = (op.expand_k || op.fold_kw) ? 3 : op.cin, cout = op.cout;
+  const int taps = op.expand_k ? 1 : op.fold_kw ? K : K * K;
   auto slot = [&](int t, int ci, int& tap, int& cidx) {
     if (op.expand_k) { tap = 0; cidx = (t / K) * op.expand_blk + (t % K) * 4 + ci; }
+    // tap row kh; "channel" = window pixel * 8 + c.  The window of output pixel x starts at image pixel x - 3, tap column
+    // kw reads image pixel x + kw - (K-1)/2, i.e. window pixel kw + 3 - (K-1)/2
+    else if (op.fold_kw) { tap = t / K; cidx = (t % K + 3 - (K - 1) / 2) * 8 + ci; }
     else { tap = t; cidx = ci; }
   };
   if (cb.empty() || cb[0].shape.size() != 4 || cb[0].shape[0] != cout || cb[0].shape[1] != cin || cb[0].shape[2] != K ||
@@ -144,18 +147,41 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
         if (iv.cs == 4 && iv.c == 3 && act_ == DType::F16 && opt_.engine != SIVO_ENGINE_SIMT && (ly.kernel == 7 || ly.kernel == 3) &&
             ly.num_output % 64 == 0 && !(no_tc && no_tc[0] == '1')) {
           // 3-channel first layer: expand the KxK taps into channels once, then it is a 1x1 tensor-core convolution
-          const int blk = (ly.kernel * 4 + 15) / 16 * 16, cs_e = round_up(ly.kernel * blk, 64);
+          const char* no_fold = std::getenv("SIVO_B200_NO_FOLD");
           Op ex;
           ex.kind = Op::Expand;
-          ex.layer = ly.name + "/expand";
           ex.in = in;
           ex.k = ly.kernel;
-          ex.expand_blk = blk;
-          ex.out = add_tensor("__expand_" + ly.name, iv.n, cs_e, iv.h, iv.w, cs_e, act_);
-          ops_.push_back(std::move(ex));
-          op.in = ops_.back().out;
-          op.expand_k = ly.kernel; op.expand_blk = blk;
-          op.k = 1; op.pad = 0; op.cin = cs_e; op.cin_p = cs_e;
+          if (no_fold && no_fold[0] == '1') {
+            // (A/B switch) materialise the taps as channels once, then it is a 1x1 tensor-core convolution
+            const int blk = (ly.kernel * 4 + 15) / 16 * 16, cs_e = round_up(ly.kernel * blk, 64);
+            ex.layer = ly.name + "/expand";
+            ex.expand_blk = blk;
+            ex.out = add_tensor("__expand_" + ly.name, iv.n, cs_e, iv.h, iv.w, cs_e, act_);
+            ops_.push_back(std::move(ex));
+            op.in = ops_.back().out;
+            op.expand_k = ly.kernel; op.expand_blk = blk;
+            op.k = 1; op.pad = 0; op.cin = cs_e; op.cin_p = cs_e;
+          } else {
+            // zero-pad to 8-channel pixels; the convolution's TMA reads overlapping 8-pixel windows of it (K x 1 layer)
+            ex.layer = ly.name + "/pad8";
+            ex.out = add_tensor("__pad8_" + ly.name, iv.n, 8, iv.h, iv.w + 8, 8, act_);
+            const size_t no = ops_.size();
+            if (!opt_.keep_blobs && no >= 2 && ops_[no - 1].kind == Op::LRN && ops_[no - 1].out == in && ops_[no - 2].kind == Op::Input &&
+                ops_[no - 2].out == ops_[no - 1].in && iv.n == 1) {
+              // input -> LRN -> pad8 collapse into one pass (the 'data' and 'norm' blobs are not materialised)
+              ex.kind = Op::InputPad8;
+              ex.lrn_size = ops_[no - 1].lrn_size; ex.lrn_alpha = ops_[no - 1].lrn_alpha;
+              ex.lrn_beta = ops_[no - 1].lrn_beta; ex.lrn_k = ops_[no - 1].lrn_k;
+              ex.layer = "input+" + ops_[no - 1].layer + "+" + ex.layer;
+              ops_.pop_back();
+              ops_.pop_back();
+            }
+            ops_.push_back(std::move(ex));
+            op.in = ops_.back().out;
+            op.fold_kw = ly.kernel;
+            op.cin = 64; op.cin_p = 64;
+          }
         }
         const TensorView civ = tensors_[op.in]->v;  // the tensor the convolution actually reads
         op.cout_p = round_up(op.cout, 64);
@@ -201,6 +227,8 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
             conv_tc_supported(op, civ, tensors_[op.out]->v)) {
           op.tc = conv_tc_plan(op, civ, tensors_[op.out]->v, op.w_tc.p);
           op.use_tc = true;
+        } else if (op.fold_kw) {
+          fail(SIVO_EINVAL, "layer '%s': window-folded first layer is not supported by the tensor-core kernel", ly.name.c_str());
         } else if (opt_.engine == SIVO_ENGINE_TCGEN05 && op.cin_p % 64 == 0 && !logits) {
           fail(SIVO_EINVAL, "layer '%s': tcgen05 engine requested but the shape is not supported", ly.name.c_str());
         }
@@ -348,7 +376,11 @@ void SegNet::enqueue(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_
         launch_input_u8(bgr_dev, tensors_[op.out]->v, s);
         break;
       case Op::Expand:
-        launch_expand_taps(tensors_[op.in]->v, tensors_[op.out]->v, op.k, op.expand_blk, s);
+      case Op::InputPad8:
+        if (op.kind == Op::InputPad8)
+          launch_input_lrn_pad8(bgr_dev, tensors_[op.out]->v, op.lrn_size, op.lrn_alpha, op.lrn_beta, op.lrn_k, s);
+        else if (op.expand_blk) launch_expand_taps(tensors_[op.in]->v, tensors_[op.out]->v, op.k, op.expand_blk, s);
+        else launch_pad8(tensors_[op.in]->v, tensors_[op.out]->v, s);
         break;
       case Op::LRN:
         launch_lrn(tensors_[op.in]->v, tensors_[op.out]->v, op.lrn_size, op.lrn_alpha, op.lrn_beta, op.lrn_k, s);

@@ -25,7 +25,7 @@ struct Tensor {
 };
 
 struct Op {
-  enum Kind { Input, LRN, Expand, Conv, Pool, Unpool, Dropout, Reduce } kind = Input;
+  enum Kind { Input, LRN, Expand, InputPad8, Conv, Pool, Unpool, Dropout, Reduce } kind = Input;
   std::string layer;
   int in = -1, in2 = -1, out = -1, out2 = -1;
   // LRN
@@ -33,6 +33,7 @@ struct Op {
   float lrn_alpha = 1.f, lrn_beta = 0.75f, lrn_k = 1.f;
   // Conv
   int k = 0, pad = 0, cin = 0, cout = 0, cin_p = 0, cout_p = 0;
+  int fold_kw = 0;                  // > 0: KxK conv over 3 channels run as a Kx1 conv over the window-folded padded input (conv_tc.cu)
   int expand_k = 0, expand_blk = 0;  // > 0: a KxK conv over 3 channels run as a 1x1 conv over the tap-expanded input
   bool relu = false, has_bn = false;
   float slope = 0.f;

@@ -397,6 +397,48 @@ __global__ void k_expand_taps(const AT* __restrict__ in, AT* __restrict__ out, i
   }
 }
 
+// Window-folded first layer (conv_tc.cu): the 4-channel half image, zero-padded to [H][W + 8] pixels of 8 channels.
+__global__ void k_pad8(const uint2* __restrict__ in, uint4* __restrict__ out, int NH, int W) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int Wp = W + 8;
+  if (i >= static_cast<size_t>(NH) * Wp) return;
+  const int xp = static_cast<int>(i % Wp);
+  const size_t row = i / Wp;
+  const int x = xp - 3;
+  uint2 v = make_uint2(0u, 0u);
+  if (x >= 0 && x < W) v = __ldg(in + row * W + x);
+  out[i] = make_uint4(v.x, v.y, 0u, 0u);
+}
+
+// k_input_u8 -> k_lrn<__half> -> k_pad8 in one pass over the padded image: identical operations on identical values
+// (the u8 -> half conversion is exact, the LRN output is rounded to half once), hence bitwise the same operand.
+__global__ void k_input_lrn_pad8(const uint8_t* __restrict__ bgr, uint4* __restrict__ out, int H, int W, int size,
+                                 float alpha_over_size, float beta, float k) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int Wp = W + 8;
+  if (i >= static_cast<size_t>(H) * Wp) return;
+  const int x = static_cast<int>(i % Wp) - 3;
+  const size_t row = i / Wp;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (x >= 0 && x < W) {
+    const uint8_t* s = bgr + 3 * (row * W + x);
+    const float in[3] = {static_cast<float>(s[0]), static_cast<float>(s[1]), static_cast<float>(s[2])};
+    const int pre = (size - 1) / 2;
+    __half o[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float acc = 0.f;
+      for (int j = ch - pre; j <= ch - pre + size - 1; ++j)
+        if (j >= 0 && j < 3) acc = __fadd_rn(acc, __fmul_rn(in[j], in[j]));
+      const float scale = __fadd_rn(k, __fmul_rn(acc, alpha_over_size));
+      o[ch] = __float2half_rn(__fmul_rn(in[ch], powf(scale, -beta)));
+    }
+    v.x = static_cast<uint32_t>(__half_as_ushort(o[0])) | (static_cast<uint32_t>(__half_as_ushort(o[1])) << 16);
+    v.y = static_cast<uint32_t>(__half_as_ushort(o[2]));
+  }
+  out[i] = v;
+}
+
 // ---- layout converters for the test hooks
 template <typename AT>
 __global__ void k_nchw_to_act(const float* __restrict__ src, AT* __restrict__ dst, int N, int C, int HW, int cs) {
@@ -506,6 +548,21 @@ void launch_expand_taps(TensorView in, TensorView out, int K, int blk, cudaStrea
   size_t total = static_cast<size_t>(out.n) * out.h * out.w * (out.cs / blk);
   DISPATCH_AT(in.dt, (k_expand_taps<AT><<<blocks_for(total, 256), 256, 0, s>>>(static_cast<const AT*>(in.p), static_cast<AT*>(out.p),
                                                                                out.n, out.h, out.w, K, blk, out.cs)));
+  SIVO_CUDA(cudaGetLastError());
+}
+
+void launch_pad8(TensorView in, TensorView out, cudaStream_t s) {
+  if (in.dt != DType::F16 || in.cs != 4 || out.cs != 8 || out.w != in.w + 8) fail(SIVO_EINVAL, "pad8: unexpected tensor layout");
+  const size_t total = static_cast<size_t>(out.n) * out.h * out.w;
+  k_pad8<<<blocks_for(total, 256), 256, 0, s>>>(static_cast<const uint2*>(in.p), static_cast<uint4*>(out.p), in.n * in.h, in.w);
+  SIVO_CUDA(cudaGetLastError());
+}
+
+void launch_input_lrn_pad8(const uint8_t* bgr, TensorView out, int size, float alpha, float beta, float k, cudaStream_t s) {
+  if (out.dt != DType::F16 || out.cs != 8 || out.n != 1) fail(SIVO_EINVAL, "input_lrn_pad8: unexpected tensor layout");
+  const size_t total = static_cast<size_t>(out.h) * out.w;
+  k_input_lrn_pad8<<<blocks_for(total, 256), 256, 0, s>>>(bgr, static_cast<uint4*>(out.p), out.h, out.w - 8, size,
+                                                          alpha / static_cast<float>(size), beta, k);
   SIVO_CUDA(cudaGetLastError());
 }
 
