@@ -361,6 +361,7 @@ int sivo_dbg_conv(int device, int engine, int precision, const float* in, int n,
     if (bias) std::copy(bias, bias + cout, b.begin());
     if (bn_scale) std::copy(bn_scale, bn_scale + cout, sc.begin());
     if (bn_shift) std::copy(bn_shift, bn_shift + cout, sh.begin());
+    op.h_bias = b; op.h_bn_scale = sc; op.h_bn_shift = sh;
     op.w_simt.alloc(ws.size() * 4);
     op.w_tc.alloc(wt.size() * 2);
     op.bias.alloc(b.size() * 4);

@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -51,9 +52,6 @@ struct TcParams {
   int strips;              // ceil(W / 128)
   int relu, has_bn, has_drop;
   float slope;
-  const float* bias;
-  const float* bn_scale;
-  const float* bn_shift;
   void* out;
   // dropout fused into the epilogue (decoder convs of Basic: decdrop4 / decdrop3)
   uint64_t seed;
@@ -70,10 +68,17 @@ struct TcParams {
   uint8_t* pool_mask;      // same shape
   // 1x1 classifier fused into the epilogue (the layer feeding Softmax): logits[j] = cls_b[j] + sum_c half(out[c]) * cls_w[c][j];
   // the 64-channel output itself is then never written
-  const float* cls_w;      // [64][cls_stride] float (half-rounded values), j < 16 used
-  const float* cls_b;      // [16]
+  int has_cls;
   float* cls_out;          // [N][H][W][16]
-  int cls_stride;
+};
+
+// Per-layer constants, passed by value as a kernel parameter so that the epilogue reads them from the constant bank
+// (FFMA operands / LDC) instead of through L1 or shared memory, whose data path the MMA operand reads saturate.
+constexpr int kMaxCout = 512;
+struct TcConsts {
+  float bias[kMaxCout], bn_scale[kMaxCout], bn_shift[kMaxCout];
+  float cls_w[64 * 16];    // fused classifier: [cin][16] float (half-rounded values), j >= classes zero
+  float cls_b[16];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -170,138 +175,179 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 4 x 4 transpose of 16-byte elements across each aligned group of four lanes: on entry lane c (of its group) holds
+// e[0..3] = chunks 0..3 of its own pixel; on return e[j] = chunk c of the group's pixel j.  After it, one store
+// instruction writes 64 contiguous bytes per pixel for 8 pixels instead of 16 bytes for 32: the epilogue's global
+// stores share the L1 / shared-memory data path with the MMA operand reads, and a warp store that touches 32
+// different lines holds that path four times longer (profiles/r1_notes.md).
+template <typename V4>
+__device__ __forceinline__ void quad_transpose(V4 (&e)[4], int lane) {
+  static_assert(sizeof(V4) == 16, "16-byte elements");
+  const bool odd = lane & 1, hi = lane & 2;
+  auto xchg = [](V4 v, int m) {
+    uint4 u = *reinterpret_cast<uint4*>(&v);
+    u.x = __shfl_xor_sync(0xffffffffu, u.x, m);
+    u.y = __shfl_xor_sync(0xffffffffu, u.y, m);
+    u.z = __shfl_xor_sync(0xffffffffu, u.z, m);
+    u.w = __shfl_xor_sync(0xffffffffu, u.w, m);
+    return *reinterpret_cast<V4*>(&u);
+  };
+#pragma unroll
+  for (int s = 0; s < 4; s += 2) {
+    const V4 got = xchg(odd ? e[s] : e[s + 1], 1);
+    if (odd) e[s] = got; else e[s + 1] = got;
+  }
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const V4 got = xchg(hi ? e[s] : e[s + 2], 2);
+    if (hi) e[s] = got; else e[s + 2] = got;
+  }
+}
+
 // One output row of the epilogue for one thread (= one pixel x of row y): reads its accumulator columns from TMEM and
 // applies the runtime-selected tail (see the file header).  `trow` = TMEM address of this row's first column for the
-// thread's lane quarter, `n0` = first output channel of the CTA's tile.
-__device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t trow, const float* s_cls, int img, int y, int x, int n0) {
+// thread's lane quarter, `n0` = first output channel of the CTA's tile.  Bias / BN / classifier constants come from the
+// kernel parameters (constant bank): loads through L1 or shared memory would compete with the MMA operand reads.
+// Must be called by all 32 lanes (warp shuffles); out-of-image pixels are masked at the stores.
+__device__ __forceinline__ void epilogue_row(const TcParams& p, const TcConsts& cst, uint32_t trow, int img, int y, int x, int n0, int lane) {
     if (p.dbg_noepi == 1) return;
     if (p.dbg_noepi == 2) {
       for (int cc = 0; cc < p.n_tile; cc += 32) { uint32_t v[32]; tmem_ld32(trow + cc, v); if (v[0] == 0x12345678u && v[31] == 0x9abcdef0u) p.cls_out[0] = 1.f; }
       return;
     }
     if (p.dbg_noepi == 3) x += 1 << 20;  // every store is predicated off by the x < W test
+    const int cl = lane & 3;          // this lane's 16-byte chunk after the transpose
+    const int xg = x - cl;            // first pixel of the lane's group of four
+    const bool row_ok = y < p.H;
     if (p.out_f32) {  // 16-channel float logits (the convolution feeding Softmax)
       uint32_t v[32];
       tmem_ld16(trow, v);
-      if (y < p.H && x < p.W) {
-        float f[16];
+      float4 e[4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float t = __fadd_rn(__uint_as_float(v[i]), __ldg(p.bias + i));
-          if (p.has_bn) t = __fadd_rn(__fmul_rn(t, __ldg(p.bn_scale + i)), __ldg(p.bn_shift + i));
-          if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
-          f[i] = t;
-        }
-        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * 16);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+      for (int i = 0; i < 16; ++i) {
+        float t = __fadd_rn(__uint_as_float(v[i]), cst.bias[i]);
+        if (p.has_bn) t = __fadd_rn(__fmul_rn(t, cst.bn_scale[i]), cst.bn_shift[i]);
+        if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
+        reinterpret_cast<float*>(&e[i >> 2])[i & 3] = t;
       }
+      quad_transpose(e, lane);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (row_ok && xg + j < p.W)
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ((static_cast<size_t>(img) * p.H + y) * p.W + xg + j) * 16 + 4 * cl) = e[j];
       return;
     }
-    if (p.cls_w) {  // conv (+bias) -> half rounding (as the unfused path stores it) -> 1x1 classifier -> float logits
+    if (p.has_cls) {  // conv (+bias) -> half rounding (as the unfused path stores it) -> 1x1 classifier -> float logits
       float l[16];
 #pragma unroll
-      for (int jj = 0; jj < 16; ++jj) l[jj] = __ldg(p.cls_b + jj);
+      for (int jj = 0; jj < 16; ++jj) l[jj] = cst.cls_b[jj];
+#pragma unroll
       for (int cc = 0; cc < 64; cc += 32) {
         uint32_t v[32];
         tmem_ld32(trow + cc, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float t = __fadd_rn(__uint_as_float(v[i]), __ldg(p.bias + cc + i));
-          if (p.has_bn) t = __fadd_rn(__fmul_rn(t, __ldg(p.bn_scale + cc + i)), __ldg(p.bn_shift + cc + i));
+          float t = __fadd_rn(__uint_as_float(v[i]), cst.bias[cc + i]);
+          if (p.has_bn) t = __fadd_rn(__fmul_rn(t, cst.bn_scale[cc + i]), cst.bn_shift[cc + i]);
           if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
           const float hv = __half2float(__float2half_rn(t));
-          const float4* w4 = reinterpret_cast<const float4*>(s_cls + (cc + i) * 16);
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 w = w4[q4];
-            l[4 * q4] = fmaf(hv, w.x, l[4 * q4]);
-            l[4 * q4 + 1] = fmaf(hv, w.y, l[4 * q4 + 1]);
-            l[4 * q4 + 2] = fmaf(hv, w.z, l[4 * q4 + 2]);
-            l[4 * q4 + 3] = fmaf(hv, w.w, l[4 * q4 + 3]);
-          }
+          for (int jj = 0; jj < 16; ++jj) l[jj] = fmaf(hv, cst.cls_w[(cc + i) * 16 + jj], l[jj]);
         }
       }
-      if (y < p.H && x < p.W) {
-        float4* dst = reinterpret_cast<float4*>(p.cls_out + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * 16);
+      float4 e[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = make_float4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
-      }
+      for (int i = 0; i < 4; ++i) e[i] = make_float4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
+      quad_transpose(e, lane);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (row_ok && xg + j < p.W)
+          *reinterpret_cast<float4*>(p.cls_out + ((static_cast<size_t>(img) * p.H + y) * p.W + xg + j) * 16 + 4 * cl) = e[j];
       return;
     }
     uint32_t bits[4] = {0, 0, 0, 0};
-    // max-unpool: fetch the row's 2-bit mask codes for the first 64 channels before touching TMEM, so the (DRAM / L2)
-    // latency of the mask overlaps the accumulator loads instead of sitting in front of every 32-channel chunk
-    uint4 mrow[4] = {};
-    const bool inside = y < p.H && x < p.W;
-    if (p.unpool_mask && inside) {
-      const uint4* mp = reinterpret_cast<const uint4*>(p.unpool_mask + ((static_cast<size_t>(img % p.mask_n) * p.H + y) * p.W + x) * p.cout_total + n0);
+    // max-unpool: fetch the 2-bit mask codes of the first 64 channels before touching TMEM, so the (DRAM / L2) latency
+    // of the mask overlaps the accumulator loads.  Already in the transposed arrangement: lane (group, cl) reads the 8
+    // codes of channels [8 cl, 8 cl + 8) of each of its group's four pixels.
+    uint2 mrow[2][4] = {};
+    const size_t mask_row = (static_cast<size_t>(img % p.mask_n) * p.H + y) * p.W;
+    if (p.unpool_mask && row_ok) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) mrow[i] = __ldg(mp + i);
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (xg + j < p.W && h * 32 < p.n_tile)
+            mrow[h][j] = __ldg(reinterpret_cast<const uint2*>(p.unpool_mask + (mask_row + xg + j) * p.cout_total + n0 + h * 32 + 8 * cl));
     }
+    const bool inside = row_ok && x < p.W;
     for (int cc = 0; cc < p.n_tile; cc += 32) {
       uint32_t v[32];
       tmem_ld32(trow + cc, v);
-      if (y < p.H && x < p.W) {
-        const int c0 = n0 + cc;
-        if (p.has_drop && ((c0 & 127) == 0 || cc == 0))
-          dropout_bits128(p.seed, *p.frame, p.drop_layer, img, static_cast<uint32_t>(y * p.W + x), c0 >> 7, bits);
-        const uint32_t keep = p.has_drop ? bits[(c0 >> 5) & 3] : 0xFFFFFFFFu;
-        uint32_t packed[16];
+      const int c0 = n0 + cc;
+      if (p.has_drop && inside && ((c0 & 127) == 0 || cc == 0))
+        dropout_bits128(p.seed, *p.frame, p.drop_layer, img, static_cast<uint32_t>(y * p.W + x), c0 >> 7, bits);
+      const uint32_t keep = p.has_drop ? bits[(c0 >> 5) & 3] : 0xFFFFFFFFu;
+      uint4 e[4];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float f[2];
+      for (int i = 0; i < 32; i += 2) {
+        float f[2];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int c = c0 + i + e;
-            float t = __fadd_rn(__uint_as_float(v[i + e]), __ldg(p.bias + c));
-            if (p.has_bn) t = __fadd_rn(__fmul_rn(t, __ldg(p.bn_scale + c)), __ldg(p.bn_shift + c));
-            if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
-            f[e] = t;
-          }
-          __half2 h = __floats2half2_rn(f[0], f[1]);
-          if (p.has_drop) {  // y = x * keep * 2 on the stored half value (exact)
-            __half2 s = __floats2half2_rn((keep >> i) & 1u ? p.drop_scale : 0.f, (keep >> (i + 1)) & 1u ? p.drop_scale : 0.f);
-            h = __hmul2(h, s);
-          }
-          packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        for (int k = 0; k < 2; ++k) {
+          const int c = c0 + i + k;
+          float t = __fadd_rn(__uint_as_float(v[i + k]), cst.bias[c]);
+          if (p.has_bn) t = __fadd_rn(__fmul_rn(t, cst.bn_scale[c]), cst.bn_shift[c]);
+          if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
+          f[k] = t;
         }
-        if (p.unpool_mask) {
-          uint4 m0, m1;
-          if (cc == 0) { m0 = mrow[0]; m1 = mrow[1]; }
-              else if (cc == 32) { m0 = mrow[2]; m1 = mrow[3]; }
+        __half2 h = __floats2half2_rn(f[0], f[1]);
+        if (p.has_drop) {  // y = x * keep * 2 on the stored half value (exact)
+          __half2 sc = __floats2half2_rn((keep >> i) & 1u ? p.drop_scale : 0.f, (keep >> (i + 1)) & 1u ? p.drop_scale : 0.f);
+          h = __hmul2(h, sc);
+        }
+        reinterpret_cast<uint32_t*>(&e[i >> 3])[(i >> 1) & 3] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      quad_transpose(e, lane);  // e[j] = channels [c0 + 8 cl, c0 + 8 cl + 8) of pixel xg + j
+      if (p.unpool_mask) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint2 m;
+          if (cc == 0) m = mrow[0][j];
+          else if (cc == 32) m = mrow[1][j];
           else {
-            const uint4* mp = reinterpret_cast<const uint4*>(p.unpool_mask + ((static_cast<size_t>(img % p.mask_n) * p.H + y) * p.W + x) * p.cout_total + c0);
-            m0 = __ldg(mp); m1 = __ldg(mp + 1);
+            m = make_uint2(0u, 0u);
+            if (row_ok && xg + j < p.W)
+              m = __ldg(reinterpret_cast<const uint2*>(p.unpool_mask + (mask_row + xg + j) * p.cout_total + c0 + 8 * cl));
           }
-          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};  // 32 mask bytes, channel order
+          if (!(row_ok && xg + j < p.W)) continue;
+          const uint32_t mw[2] = {m.x, m.y};                               // 8 mask bytes, channel order
+          const uint32_t ew[4] = {e[j].x, e[j].y, e[j].z, e[j].w};         // half2 i = channels 2i, 2i+1 -> mask bytes 2i, 2i+1
 #pragma unroll
           for (int pos = 0; pos < 4; ++pos) {
-            uint32_t sel[16];
+            uint32_t sel[4];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {  // half2 i holds channels 2i, 2i+1 -> mask bytes 2i, 2i+1
+            for (int i = 0; i < 4; ++i) {
               const uint32_t mb = mw[i >> 1] >> ((i & 1) * 16);
               const uint32_t lo = ((mb & 0xFFu) == static_cast<uint32_t>(pos)) ? 0x0000FFFFu : 0u;
-              const uint32_t hi = (((mb >> 8) & 0xFFu) == static_cast<uint32_t>(pos)) ? 0xFFFF0000u : 0u;
-              sel[i] = packed[i] & (lo | hi);
+              const uint32_t hi2 = (((mb >> 8) & 0xFFu) == static_cast<uint32_t>(pos)) ? 0xFFFF0000u : 0u;
+              sel[i] = ew[i] & (lo | hi2);
             }
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) +
-                ((static_cast<size_t>(img) * 2 * p.H + 2 * y + (pos >> 1)) * (2 * p.W) + 2 * x + (pos & 1)) * p.cout_total + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(sel[4 * i], sel[4 * i + 1], sel[4 * i + 2], sel[4 * i + 3]);
+            *reinterpret_cast<uint4*>(static_cast<__half*>(p.out) +
+                ((static_cast<size_t>(img) * 2 * p.H + 2 * y + (pos >> 1)) * (2 * p.W) + 2 * (xg + j) + (pos & 1)) * p.cout_total + c0 + 8 * cl) =
+                make_uint4(sel[0], sel[1], sel[2], sel[3]);
           }
-        } else {
-          uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout_total + c0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
         }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (row_ok && xg + j < p.W)
+            *reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + ((static_cast<size_t>(img) * p.H + y) * p.W + xg + j) * p.cout_total + c0 + 8 * cl) = e[j];
       }
     }
 }
 
 // Two vertically adjacent output rows (y even) with the pooling epilogue: bias / BN / ReLU -> half (the value the
 // unfused path would store) -> 2x2 max with first-maximum argmax; the horizontal neighbour lives in the adjacent lane.
-__device__ __forceinline__ void epilogue_pool_rows(const TcParams& p, uint32_t trow0, uint32_t trow1, int img, int y, int x, int n0, int lane) {
+__device__ __forceinline__ void epilogue_pool_rows(const TcParams& p, const TcConsts& cst, uint32_t trow0, uint32_t trow1, int img, int y, int x, int n0, int lane) {
   if (p.dbg_noepi) return;
   const bool writer = (lane & 1) == 0 && y + 1 < p.H && x + 1 < p.W;
   for (int cc = 0; cc < p.n_tile; cc += 32) {
@@ -321,8 +367,8 @@ __device__ __forceinline__ void epilogue_pool_rows(const TcParams& p, uint32_t t
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int c = c0 + i + e;
-          float t = __fadd_rn(__uint_as_float(r ? v1[i + e] : v0[i + e]), __ldg(p.bias + c));
-          if (p.has_bn) t = __fadd_rn(__fmul_rn(t, __ldg(p.bn_scale + c)), __ldg(p.bn_shift + c));
+          float t = __fadd_rn(__uint_as_float(r ? v1[i + e] : v0[i + e]), cst.bias[c]);
+          if (p.has_bn) t = __fadd_rn(__fmul_rn(t, cst.bn_scale[c]), cst.bn_shift[c]);
           if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
           f[e] = t;
         }
@@ -364,7 +410,8 @@ __device__ __forceinline__ void epilogue_pool_rows(const TcParams& p, uint32_t t
 //               8-channel window starting at it, so a 3-channel K x K layer is a K x 1 layer; see conv_tc_plan).
 template <int K, bool ROLL, int kRows, int KW = K>
 __global__ void __launch_bounds__(kTcThreads, 1)
-k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcParams p,
+          const __grid_constant__ TcConsts cst) {
   constexpr int RK = kRows + K - 1;                  // halo rows one row pair reads (per chunk)
   constexpr int kSlots = ROLL ? RK : 2 * RK;         // ROLL: rows are released as soon as their last tap row is issued
   constexpr int kPad = (K - 1) / 2, kPadW = (KW - 1) / 2;
@@ -383,7 +430,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint64_t* t_full = b_empty + kBStages;         // [2]
   uint64_t* t_empty = t_full + 2;                // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-  float* s_cls = reinterpret_cast<float*>(tmem_slot + 4);  // [64][16] classifier weights (only when p.cls_w)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int strip = blockIdx.x % p.strips, rowblk = blockIdx.x / p.strips;
@@ -407,8 +453,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (p.cls_w)
-    for (int e = threadIdx.x; e < 64 * 16; e += kTcThreads) s_cls[e] = p.cls_w[(e >> 4) * p.cls_stride + (e & 15)];
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -547,7 +591,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         if (kRows == 4 || eset == 0) {  // a row pair per set (kRows == 2: one pair, taken by set 0)
           const int r = kRows == 4 ? 2 * eset : 0;
           const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
-          epilogue_pool_rows(p, trow, trow + p.n_tile, img, y_base + j * kRows + r, x, n0, lane);
+          epilogue_pool_rows(p, cst, trow, trow + p.n_tile, img, y_base + j * kRows + r, x, n0, lane);
         }
       } else {
 #pragma unroll
@@ -555,7 +599,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           const int r = eset * kPer + rr;
           const int y = y_base + j * kRows + r;
           const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
-          epilogue_row(p, trow, s_cls, img, y, x, n0);
+          epilogue_row(p, cst, trow, img, y, x, n0, lane);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -580,7 +624,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // instructions.  Weights come as [kw][kh][cout][cin] so one TMA box of 128 rows lands both taps of a pair.
 template <int K>
 __global__ void __launch_bounds__(kTcThreads, 1)
-k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcParams p,
+               const __grid_constant__ TcConsts cst) {
   constexpr int kRows = 4, RK = kRows + K - 1, kSlots = RK, kPad = (K - 1) / 2, NP = (K + 1) / 2;
   constexpr int kBBytes = 128 * 128;  // two stacked 64 x 64 weight tiles
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -596,7 +641,6 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* t_full = b_empty + kBStages;
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-  float* s_cls = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int strip = blockIdx.x % p.strips, rowblk = blockIdx.x / p.strips;
@@ -616,8 +660,6 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (p.cls_w)
-    for (int e = threadIdx.x; e < 64 * 16; e += kTcThreads) s_cls[e] = p.cls_w[(e >> 4) * p.cls_stride + (e & 15)];
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -748,14 +790,14 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (p.pool_out) {  // accumulators sit in decreasing row order: row r+1 is 64 columns below row r
         const int r = 2 * eset;
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + (3 - r)) * 64);
-        epilogue_pool_rows(p, trow, trow - 64, img, y_base + j * kRows + r, x, 0, lane);
+        epilogue_pool_rows(p, cst, trow, trow - 64, img, y_base + j * kRows + r, x, 0, lane);
       } else {
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
           const int r = 2 * eset + rr;
           const int y = y_base + j * kRows + r;
           const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + (3 - r)) * 64);
-          epilogue_row(p, trow, s_cls, img, y, x, 0);
+          epilogue_row(p, cst, trow, img, y, x, 0, lane);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -800,6 +842,7 @@ void encode(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const 
 struct ConvTcPlan {
   CUtensorMap map_a, map_b;
   TcParams p;
+  TcConsts cst;
   dim3 grid;
   size_t smem;
   int k, rows;
@@ -816,7 +859,7 @@ void conv_tc_dispatch(const ConvTcPlan& plan, cudaStream_t s, bool configure) {
     // the limit is per kernel function, not per launch: always raise it to the full 227 KB so that plans of different
     // sizes that share an instantiation (e.g. the 16-wide logits tile and a 64-wide layer) cannot lower it for each other
     if (configure) SIVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    else kern<<<plan.grid, kTcThreads, plan.smem, s>>>(plan.map_a, plan.map_b, plan.p);
+    else kern<<<plan.grid, kTcThreads, plan.smem, s>>>(plan.map_a, plan.map_b, plan.p, plan.cst);
   };
   const int K = plan.k;
   if (plan.pair) { if (K == 7) go(k_conv_tc_pair<7>); else go(k_conv_tc_pair<3>); }
@@ -862,6 +905,7 @@ bool conv_tc_supported(const Op& op, const TensorView& in, const TensorView& out
   if (const char* e = std::getenv("SIVO_B200_NO_TC")) if (e[0] == '1') return false;
   if (in.dt != DType::F16) return false;
   if (op.k != 1 && op.k != 3 && op.k != 7) return false;
+  if (op.cout_p > kMaxCout) return false;
   if (op.fold_kw) {
     if (in.cs != 8 || op.cin_p != 64 || (op.k != 3 && op.k != 7) || out.dt != DType::F16 || op.cout % 64 || out.cs != op.cout) return false;
     return tc_stages(op.k, true, tc_pick_n(op, out, true)) > 0;
@@ -939,9 +983,15 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   }
   p.pairs_per_cta = ppc;
   p.relu = op.relu; p.has_bn = op.has_bn; p.slope = op.slope;
-  p.bias = op.bias.as<float>();
-  p.bn_scale = op.has_bn ? op.bn_scale.as<float>() : nullptr;
-  p.bn_shift = op.has_bn ? op.bn_shift.as<float>() : nullptr;
+  std::memset(&plan->cst, 0, sizeof(TcConsts));
+  if (static_cast<int>(op.h_bias.size()) != op.cout_p || (op.has_bn && (static_cast<int>(op.h_bn_scale.size()) != op.cout_p ||
+                                                                         static_cast<int>(op.h_bn_shift.size()) != op.cout_p)))
+    fail(SIVO_EINVAL, "conv_tc_plan: host copies of the bias / BN constants are missing");
+  std::copy(op.h_bias.begin(), op.h_bias.end(), plan->cst.bias);
+  if (op.has_bn) {
+    std::copy(op.h_bn_scale.begin(), op.h_bn_scale.end(), plan->cst.bn_scale);
+    std::copy(op.h_bn_shift.begin(), op.h_bn_shift.end(), plan->cst.bn_shift);
+  }
   p.out = out.p;
   p.has_drop = 0; p.seed = 0; p.frame = nullptr; p.drop_layer = 0; p.drop_scale = 2.f;
   p.unpool_mask = nullptr; p.mask_n = 1;
@@ -950,7 +1000,7 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   if (const char* e = std::getenv("SIVO_B200_TC_NOEPI")) p.dbg_noepi = atoi(e);
   if (const char* e = std::getenv("SIVO_B200_TC_NOSHIFT")) p.dbg_noshift = e[0] == '1';
   p.pool_out = nullptr; p.pool_mask = nullptr;
-  p.cls_w = nullptr; p.cls_b = nullptr; p.cls_out = nullptr; p.cls_stride = 0;
+  p.has_cls = 0; p.cls_out = nullptr;
   plan->grid = dim3(p.strips * ceil_div(total_pairs, ppc), cout_tiles, in.n);
   p.b_stages = tc_stages(K, roll, n_tile);
   if (const char* e = std::getenv("SIVO_B200_TC_BSTAGES")) p.b_stages = std::max(2, std::min(p.b_stages, atoi(e)));  // experiment knob
@@ -1015,7 +1065,7 @@ std::vector<__half> conv_tc_pair_weights(const float* w_cout_cin_k_k, int K) {
 }
 
 bool conv_tc_can_fuse_pool(const ConvTcPlan& plan) {
-  return !plan.p.out_f32 && !plan.p.unpool_mask && !plan.p.has_drop && !plan.p.cls_w && (plan.p.H % 2) == 0 && (plan.p.W % 2) == 0;
+  return !plan.p.out_f32 && !plan.p.unpool_mask && !plan.p.has_drop && !plan.p.has_cls && (plan.p.H % 2) == 0 && (plan.p.W % 2) == 0;
 }
 
 void conv_tc_set_pool(ConvTcPlan& plan, void* pooled, uint8_t* mask) {
@@ -1027,10 +1077,11 @@ bool conv_tc_can_fuse_classifier(const ConvTcPlan& plan) {
   return plan.roll && plan.p.n_tile == 64 && plan.p.cout_total == 64 && !plan.p.out_f32 && !plan.p.unpool_mask && !plan.p.has_drop && !plan.p.pool_out;
 }
 
-void conv_tc_set_classifier(ConvTcPlan& plan, const float* w_cin_by_cout, int stride, const float* bias, float* logits) {
-  plan.p.cls_w = w_cin_by_cout;
-  plan.p.cls_stride = stride;
-  plan.p.cls_b = bias;
+void conv_tc_set_classifier(ConvTcPlan& plan, const float* w_cin_by_cout, int stride, const float* bias, int n_bias, float* logits) {
+  for (int c = 0; c < 64; ++c)
+    for (int j = 0; j < 16; ++j) plan.cst.cls_w[c * 16 + j] = j < stride ? w_cin_by_cout[static_cast<size_t>(c) * stride + j] : 0.f;
+  for (int j = 0; j < 16; ++j) plan.cst.cls_b[j] = j < n_bias ? bias[j] : 0.f;
+  plan.p.has_cls = 1;
   plan.p.cls_out = logits;
 }
 

@@ -245,7 +245,8 @@ Orb::Orb(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th,
     // they slot in ahead of the next wave of a long convolution kernel running on the same GPU
     int lo = 0, hi = 0;
     SIVO_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    SIVO_CUDA(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, hi));
+    const char* e = std::getenv("SIVO_B200_ORB_PRIO");  // A/B switch: 0 = default priority
+    SIVO_CUDA(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, (e && e[0] == '0') ? lo : hi));
   }
   for (auto& e : ev_) SIVO_CUDA(cudaEventCreate(&e));
   d_umax_.alloc(sizeof(tab_.umax));
@@ -343,6 +344,7 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
   if (n) *n = 0;
   if (!gray || rows <= 0 || cols <= 0) return;  // `if (_image.empty()) return;` (:1023-1024)
   if (stride < static_cast<size_t>(cols)) fail(SIVO_EINVAL, "ORBextractor: stride smaller than a row");
+  const auto w0 = std::chrono::steady_clock::now();
   SIVO_CUDA(cudaSetDevice(device_));
   ensure(rows, cols);
   const int ncells = static_cast<int>(cells_.size());
@@ -390,7 +392,10 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
     SIVO_CUDA(cudaMemcpyAsync(h_pyr_.p, d_pyr_.p, pyr_bytes_, cudaMemcpyDeviceToHost, s));
   }
   launches = nlevels_ + 5;
+  static const bool trace = [] { const char* e = std::getenv("SIVO_B200_ORB_TRACE"); return e && e[0] == '1'; }();
+  const auto w1 = std::chrono::steady_clock::now();
   SIVO_CUDA(cudaEventSynchronize(ev_[1]));
+  const auto w2 = std::chrono::steady_clock::now();
 
   const int* loff = h_level_off_.as<int>();
   const uint32_t* cand = h_cand_.as<uint32_t>();
@@ -443,7 +448,13 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
     ++launches;
   }
   SIVO_CUDA(cudaEventRecord(ev_[3], s));
+  const auto w3 = std::chrono::steady_clock::now();
   SIVO_CUDA(cudaStreamSynchronize(s));
+  if (trace) {
+    auto ms = [](auto a, auto b) { return std::chrono::duration<float, std::milli>(b - a).count(); };
+    fprintf(stderr, "[orb %p] enqueue %.3f wait1 %.3f tree %.3f enqueue2 %.3f wait2 %.3f ms, %d candidates\n", static_cast<void*>(this),
+            ms(w0, w1), ms(w1, w2), tree_ms, ms(t0, w3) - tree_ms, ms(w3, std::chrono::steady_clock::now()), loff[nlevels_]);
+  }
   float a = 0, b2 = 0;
   SIVO_CUDA(cudaEventElapsedTime(&a, ev_[0], ev_[1]));
   SIVO_CUDA(cudaEventElapsedTime(&b2, ev_[2], ev_[3]));

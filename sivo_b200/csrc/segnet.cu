@@ -56,6 +56,7 @@ void SegNet::prepare_conv(Op& op, const std::vector<Blob>& cb, const std::vector
         slot(t, ci, tap, cidx);
         ws[(static_cast<size_t>(tap) * op.cin_p + cidx) * op.cout_p + co] = half ? through_half(v) : v;
       }
+  op.h_w = ws;
   op.w_simt.alloc(ws.size() * sizeof(float));
   SIVO_CUDA(cudaMemcpy(op.w_simt.p, ws.data(), ws.size() * sizeof(float), cudaMemcpyHostToDevice));
   if (half) {  // tensor-core layout: [tap][cout_p][cin_p] half, K(=cin)-major rows
@@ -81,6 +82,7 @@ void SegNet::prepare_conv(Op& op, const std::vector<Blob>& cb, const std::vector
     if (static_cast<int>(cb[1].count()) != cout) fail(SIVO_EFORMAT, "layer '%s': bias blob size mismatch", op.layer.c_str());
     std::copy(cb[1].data.begin(), cb[1].data.end(), b.begin());
   }
+  op.h_bias = b;
   op.bias.alloc(b.size() * sizeof(float));
   SIVO_CUDA(cudaMemcpy(op.bias.p, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
   if (bn) {
@@ -89,6 +91,8 @@ void SegNet::prepare_conv(Op& op, const std::vector<Blob>& cb, const std::vector
     std::vector<float> sc(op.cout_p, 1.f), sh(op.cout_p, 0.f);
     std::copy((*bn)[0].data.begin(), (*bn)[0].data.end(), sc.begin());
     std::copy((*bn)[1].data.begin(), (*bn)[1].data.end(), sh.begin());
+    op.h_bn_scale = sc;
+    op.h_bn_shift = sh;
     op.bn_scale.alloc(sc.size() * sizeof(float));
     op.bn_shift.alloc(sh.size() * sizeof(float));
     SIVO_CUDA(cudaMemcpy(op.bn_scale.p, sc.data(), sc.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -216,7 +220,7 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
             ops_.back().kind == Op::Conv && ops_.back().use_tc && ops_.back().out == in && conv_tc_can_fuse_classifier(*ops_.back().tc)) {
           // 1x1 classifier straight after a tensor-core convolution: computed in that convolution's epilogue from the
           // half-rounded activations, so the 64-channel tensor is never written or re-read
-          conv_tc_set_classifier(*ops_.back().tc, op.w_simt.as<float>(), op.cout_p, op.bias.as<float>(),
+          conv_tc_set_classifier(*ops_.back().tc, op.h_w.data(), op.cout_p, op.h_bias.data(), std::min(16, op.cout_p),
                                  static_cast<float*>(tensors_[op.out]->v.p));
           ops_.back().layer += "+" + ly.name;
           fused_.push_back(std::move(op));
