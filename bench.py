@@ -74,42 +74,65 @@ def frames(n, start=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML from a thread every 2 ms
+    (the timed regions last tens of milliseconds, too short for `nvidia-smi -lms`), nvidia-smi as the fallback."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.rows = []
-        self.proc = None
         self.index = index
+        self.sm, self.mask, self.max_mhz, self.power = [], 0, None, []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.nvml = None
+
+    def _handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        self.nvml = pynvml
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            return pynvml.nvmlDeviceGetHandleByIndex(self.index)
+
+    def _loop(self, h):
+        nv = self.nvml
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(reasons(h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1e3)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            h = self._handle()
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(h, self.nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._loop, args=(h,), daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.thread = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        if self.thread:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+        if not self.sm:  # NVML unavailable: one nvidia-smi query (not under load -- says so)
+            try:
+                q = "clocks.sm,clocks.max.sm"
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "samples": 0, "source": "nvidia-smi after the run"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_min_mhz": float(min(self.sm)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for b, n in self.REASONS.items() if self.mask & b), "samples": len(self.sm),
+                "power_w_median": float(np.median(self.power)) if self.power else None, "source": "nvml, 2 ms period, value + e2e regions"}
 
 
 def cpu_reference_frame(net, weights, left_bgr, gl, gr, nfeatures, threads):
@@ -333,13 +356,19 @@ def main():
     cpu_base = None
     if rank == 0:
         seg.set_profiling(True)
-        conv_ms, tot_ms = [], []
+        conv_ms, tot_ms, per_op = [], [], []
         for i in range(min(args.steps, 10)):
             seg.run_device(d_bgr[i % n_frames].data_ptr(), d_cls.data_ptr(), d_conf.data_ptr(), d_ent.data_ptr(), stream.cuda_stream)
             tm = seg.last_timing()
             conv_ms.append(tm["conv_ms"])
             tot_ms.append(tm["total_ms"])
+            per_op.append(seg.op_timings())
         seg.set_profiling(False)
+        # dominant kernel = the launch with the most algorithmic flops (conv_decode1 + classifier in both models)
+        names = [o[0] for o in per_op[0]]
+        op_flops = [o[2] for o in per_op[0]]
+        op_ms = np.mean([[o[1] for o in run] for run in per_op], axis=0)
+        dom = int(np.argmax(op_flops))
         fl = seg.flops()
         peaks = {}
         try:
@@ -348,11 +377,22 @@ def main():
             pass
         peak = peaks.get("bf16_tflops_sustained") or 1400.0
         which = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF sustained (B200_PROFILING.md)"
-        ach = fl["dedup"] / (np.mean(conv_ms) * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                "kernel": "convolution layers (all conv launches of one frame)", "peak_source": which,
+        ach = op_flops[dom] / (op_ms[dom] * 1e-3) / 1e12
+        ach_all = fl["dedup"] / (np.mean(conv_ms) * 1e-3) / 1e12
+        traffic = None
+        try:  # dram bytes of that kernel from the committed `ncu --set full` capture (tools/ncu_summary.py writes it)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            traffic = tj.get(args.model, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "kernel": f"tcgen05 convolution launch '{names[dom]}'", "peak_source": which,
+                "kernel_ms": float(op_ms[dom]), "kernel_gflop": op_flops[dom] / 1e9,
+                "all_conv_launches": {"achieved": ach_all, "frac": ach_all / peak, "ms_per_frame": float(np.mean(conv_ms)),
+                                      "gflop_per_frame": fl["dedup"] / 1e9},
                 "conv_ms_per_frame": float(np.mean(conv_ms)), "segnet_ms_per_frame": float(np.mean(tot_ms)),
-                "algorithmic_gflop_per_frame": fl["dedup"] / 1e9, "naive_gflop_per_frame": fl["naive"] / 1e9}
+                "algorithmic_gflop_per_frame": fl["dedup"] / 1e9, "naive_gflop_per_frame": fl["naive"] / 1e9,
+                "launch_ms": {n: round(float(m), 4) for n, m in zip(names, op_ms)}}
         if not args.no_cpu_baseline and world == 1:
             w = weights or load_weights(net, model)
             cores = os.cpu_count() or 1

@@ -91,6 +91,10 @@ int sivo_segnet_set_profiling(sivo_segnet_t* h, int on);
 int sivo_segnet_last_timing(const sivo_segnet_t* h, float* conv_ms, float* other_ms, float* reduce_ms,
                             float* total_ms, int* launches);
 int sivo_segnet_flops(const sivo_segnet_t* h, double* conv_flops_dedup, double* conv_flops_naive);
+/* One launch of the op list (index < 0: only `*n_ops`): layer name(s) it covers, its time in the last profiled run
+ * (ms, CUDA events on the launching stream) and its algorithmic convolution flops (0 for non-convolution launches). */
+int sivo_segnet_op_timing(const sivo_segnet_t* h, int index, char* name, size_t cap, float* ms, double* flops,
+                          int* n_ops);
 void sivo_segnet_destroy(sivo_segnet_t* h);
 
 /* ---- ORB extractor ---------------------------------------------------------------------------- */

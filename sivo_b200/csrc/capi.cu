@@ -107,6 +107,20 @@ int sivo_segnet_last_timing(const sivo_segnet_t* h, float* conv_ms, float* other
   });
 }
 
+int sivo_segnet_op_timing(const sivo_segnet_t* h, int index, char* name, size_t cap, float* ms, double* flops, int* n_ops) {
+  return guarded([&] {
+    if (!h) fail(SIVO_EINVAL, "null handle");
+    const int n = static_cast<int>(h->impl->n_ops());
+    if (n_ops) *n_ops = n;
+    if (index < 0) return;  // count query
+    if (index >= n) fail(SIVO_ERANGE, "op index %d out of range (%d launches)", index, n);
+    const Op& op = h->impl->op_at(index);
+    if (name && cap) snprintf(name, cap, "%s", op.layer.c_str());
+    if (ms) *ms = static_cast<size_t>(index) < h->impl->op_ms.size() ? h->impl->op_ms[index] : 0.f;
+    if (flops) *flops = op.kind == Op::Conv ? op.flops : 0.0;
+  });
+}
+
 int sivo_segnet_flops(const sivo_segnet_t* h, double* dedup, double* naive) {
   return guarded([&] {
     if (!h) fail(SIVO_EINVAL, "null handle");

@@ -2,6 +2,11 @@
 // orb_kernels.cu.  One instance = one CUDA stream + its own workspace, so two instances can run
 // concurrently from two threads as Frame.cc:126-129 does.
 #pragma once
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.h"
@@ -99,6 +104,12 @@ class Orb {
   int cand_cap_ = 0, sel_cap_ = 0;
   std::vector<uint32_t> last_cand_;  // last call's packed candidates (x | y << 12 | resp << 24), all levels (test hook)
   std::vector<int> last_off_;        // per-level offsets into last_cand_
+  // host quad tree: the pyramid levels are independent, so they are distributed over a few persistent helper threads
+  // (largest level first); results are assembled in level order, so the output is the sequential one
+  struct TreePool;
+  std::shared_ptr<TreePool> pool_;
+  std::vector<float> lxs_[kOrbMaxLevels], lys_[kOrbMaxLevels], lrs_[kOrbMaxLevels];
+  std::vector<int> lkeep_[kOrbMaxLevels];
 };
 
 }  // namespace sivo

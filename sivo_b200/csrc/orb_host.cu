@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <string>
 
 #include "orb.h"
 
@@ -226,6 +227,58 @@ std::vector<int> orb_distribute(const float* xs, const float* ys, const float* r
 }
 
 // ---------------------------------------------------------------- Orb
+// A handful of helper threads that sleep between calls; run() hands every thread (and the caller) a share.
+struct Orb::TreePool {
+  std::vector<std::thread> threads;
+  std::mutex m;
+  std::condition_variable cv, done_cv;
+  std::function<void(int)> job;  // argument: worker index 1..threads.size() (the caller is worker 0)
+  unsigned generation = 0;
+  int pending = 0;
+  bool stop = false;
+  explicit TreePool(int helpers) {
+    for (int i = 0; i < helpers; ++i)
+      threads.emplace_back([this, i] {
+        unsigned seen = 0;
+        for (;;) {
+          std::function<void(int)> fn;
+          {
+            std::unique_lock<std::mutex> lk(m);
+            cv.wait(lk, [&] { return stop || generation != seen; });
+            if (stop) return;
+            seen = generation;
+            fn = job;
+          }
+          fn(i + 1);
+          {
+            std::lock_guard<std::mutex> lk(m);
+            if (--pending == 0) done_cv.notify_one();
+          }
+        }
+      });
+  }
+  ~TreePool() {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      stop = true;
+    }
+    cv.notify_all();
+    for (auto& t : threads) t.join();
+  }
+  void run(const std::function<void(int)>& fn) {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      job = fn;
+      pending = static_cast<int>(threads.size());
+      ++generation;
+    }
+    cv.notify_all();
+    fn(0);
+    std::unique_lock<std::mutex> lk(m);
+    done_cv.wait(lk, [&] { return pending == 0; });
+  }
+};
+
 namespace {
 std::once_flag g_pattern_once[64];
 int cv_round_f(float v) { return static_cast<int>(std::nearbyint(v)); }
@@ -238,6 +291,11 @@ Orb::Orb(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th,
     fail(SIVO_EINVAL, "ORBextractor: bad parameters (nfeatures %d, scale %.3f, levels %d, th %d/%d)", nfeatures, scale_factor,
          nlevels, ini_th, min_th);
   tab_ = orb_make_tables(nfeatures, scale_factor, nlevels);
+  {
+    int helpers = std::min(3, nlevels - 1);
+    if (const char* e = std::getenv("SIVO_B200_ORB_TREE_THREADS")) helpers = std::max(0, std::min(7, atoi(e) - 1));
+    if (helpers > 0) pool_ = std::make_shared<TreePool>(helpers);
+  }
   SIVO_CUDA(cudaSetDevice(device_));
   std::call_once(g_pattern_once[device_ & 63], [] { orb_upload_pattern(); });
   {
@@ -406,20 +464,48 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
   OrbSelected* sel = h_sel_.as<OrbSelected>();
   last_off_.assign(loff, loff + nlevels_ + 1);
   last_cand_.assign(cand, cand + loff[nlevels_]);
-  std::vector<float> xs, ys, rs;
-  for (int l = 0; l < nlevels_; ++l) {
+  const int min_b = kEdge - 3;
+  auto tree_level = [&](int l) {
     const OrbLevel& lv = lt_.lv[l];
-    const int b = loff[l], e = loff[l + 1], m = e - b;
+    const int b = loff[l], m = loff[l + 1] - b;
+    std::vector<float>&xs = lxs_[l], &ys = lys_[l], &rs = lrs_[l];
     xs.resize(m); ys.resize(m); rs.resize(m);
     for (int i = 0; i < m; ++i) {
-      uint32_t c = cand[b + i];
+      const uint32_t c = cand[b + i];
       xs[i] = static_cast<float>(c & 0xFFF);
       ys[i] = static_cast<float>((c >> 12) & 0xFFF);
       rs[i] = static_cast<float>(c >> 24);
     }
-    const int min_b = kEdge - 3;
-    std::vector<int> keep = orb_distribute(xs.data(), ys.data(), rs.data(), m, min_b, lv.w - kEdge + 3, min_b, lv.h - kEdge + 3,
-                                           tab_.per_level[l]);
+    lkeep_[l] = orb_distribute(xs.data(), ys.data(), rs.data(), m, min_b, lv.w - kEdge + 3, min_b, lv.h - kEdge + 3, tab_.per_level[l]);
+  };
+  {
+    // longest-processing-time assignment of the levels to the caller + helpers
+    const int workers = pool_ ? static_cast<int>(pool_->threads.size()) + 1 : 1;
+    int order[kOrbMaxLevels], owner[kOrbMaxLevels], load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int l = 0; l < nlevels_; ++l) order[l] = l;
+    std::sort(order, order + nlevels_, [&](int a, int b) { return loff[a + 1] - loff[a] > loff[b + 1] - loff[b]; });
+    for (int i = 0; i < nlevels_; ++i) {
+      int w = 0;
+      for (int k = 1; k < workers; ++k) if (load[k] < load[w]) w = k;
+      owner[order[i]] = w;
+      load[w] += loff[order[i] + 1] - loff[order[i]] + 64;
+    }
+    std::string worker_error;
+    std::mutex err_m;
+    auto share = [&](int w) {
+      try {
+        for (int l = 0; l < nlevels_; ++l) if (owner[l] == w) tree_level(l);
+      } catch (const std::exception& e) {
+        std::lock_guard<std::mutex> lk(err_m);
+        worker_error = e.what();
+      }
+    };
+    if (pool_) pool_->run(share); else share(0);
+    if (!worker_error.empty()) fail(SIVO_EINVAL, "ORBextractor: quad tree failed: %s", worker_error.c_str());
+  }
+  for (int l = 0; l < nlevels_; ++l) {
+    const std::vector<float>&xs = lxs_[l], &ys = lys_[l], &rs = lrs_[l];
+    const std::vector<int>& keep = lkeep_[l];
     const int scaled_patch = static_cast<int>(31 * tab_.scale[l]);  // PATCH_SIZE * mvScaleFactor[level] (:828)
     for (int k : keep) {
       sivo_keypoint kp;

@@ -178,6 +178,7 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
               ex.lrn_size = ops_[no - 1].lrn_size; ex.lrn_alpha = ops_[no - 1].lrn_alpha;
               ex.lrn_beta = ops_[no - 1].lrn_beta; ex.lrn_k = ops_[no - 1].lrn_k;
               ex.layer = "input+" + ops_[no - 1].layer + "+" + ex.layer;
+              tensors_[ops_[no - 1].out]->elided = tensors_[ops_[no - 2].out]->elided = true;
               ops_.pop_back();
               ops_.pop_back();
             }
@@ -223,6 +224,8 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
           conv_tc_set_classifier(*ops_.back().tc, op.h_w.data(), op.cout_p, op.h_bias.data(), std::min(16, op.cout_p),
                                  static_cast<float*>(tensors_[op.out]->v.p));
           ops_.back().layer += "+" + ly.name;
+          ops_.back().flops += op.flops;  // the classifier's multiply-adds run inside that launch
+          tensors_[in]->elided = true;
           fused_.push_back(std::move(op));
           li = lj - 1;
           break;
@@ -253,6 +256,7 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
             iv.dt == DType::F16 && conv_tc_can_fuse_pool(*ops_.back().tc)) {
           // the producing tensor-core convolution pools in its epilogue: the full-resolution activations are never stored
           conv_tc_set_pool(*ops_.back().tc, tensors_[pooled]->v.p, tensors_[pmask]->buf.as<uint8_t>());
+          tensors_[in]->elided = true;
           ops_.back().layer += "+" + ly.name;
           break;
         }
@@ -276,7 +280,19 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
           // the producing tensor-core convolution scatters straight into the unpooled tensor (its own output blob
           // is never materialised; keep_blobs keeps the two-kernel form so tests can read it)
           conv_tc_set_unpool(*ops_.back().tc, mt.buf.as<uint8_t>(), mt.v.n, tensors_[up]->v.p);
+          tensors_[in]->elided = true;
           ops_.back().layer += "+" + ly.name;
+          break;
+        }
+        if (!opt_.keep_blobs && !ops_.empty() && ops_.back().kind == Op::Dropout && ops_.back().out == in && iv.dt == DType::F16 &&
+            iv.cs == iv.c && iv.cs % 8 == 0) {
+          // sampling Dropout feeding the upsample: one pass writes the unpooled tensor (the dropped blob is not materialised)
+          Op& d = ops_.back();
+          tensors_[in]->elided = true;
+          d.kind = Op::DropoutUnpool;
+          d.in2 = m;
+          d.out = up;
+          d.layer += "+" + ly.name;
           break;
         }
         Op op;
@@ -420,6 +436,15 @@ void SegNet::enqueue(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_
         launch_dropout(tensors_[op.in]->v, tensors_[op.out]->v, d, op.drop_scale, s);
         break;
       }
+      case Op::DropoutUnpool: {
+        DropoutParams d;
+        d.seed = opt_.seed;
+        d.frame_dev = d_frame_.as<uint64_t>();
+        d.layer = op.drop_layer;
+        const Tensor& mt = *tensors_[op.in2];
+        launch_dropout_unpool(tensors_[op.in]->v, T_, mt.buf.as<uint8_t>(), mt.v.n, tensors_[op.out]->v, d, op.drop_scale, s);
+        break;
+      }
       case Op::Reduce: {
         const TensorView& lv = tensors_[op.in]->v;
         launch_mc_reduce(static_cast<const float*>(lv.p), lv.n, lv.c, lv.cs, lv.h * lv.w, classes_dev, conf_dev, ent_dev, s);
@@ -445,9 +470,11 @@ void SegNet::run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* co
     enqueue(bgr_dev, classes_dev, conf_dev, ent_dev, s, true);
     SIVO_CUDA(cudaEventSynchronize(events_[ops_.size()]));
     conv_ms = other_ms = reduce_ms = 0;
+    op_ms.assign(ops_.size(), 0.f);
     for (size_t i = 0; i < ops_.size(); ++i) {
       float ms = 0;
       SIVO_CUDA(cudaEventElapsedTime(&ms, events_[i], events_[i + 1]));
+      op_ms[i] = ms;
       if (ops_[i].kind == Op::Conv) conv_ms += ms;
       else if (ops_[i].kind == Op::Reduce) reduce_ms += ms;
       else other_ms += ms;
@@ -535,6 +562,8 @@ void SegNet::blob(const std::string& name, float* out, size_t cap, int* n, int* 
   auto it = by_name_.find(name);
   if (it == by_name_.end()) fail(SIVO_EINVAL, "no blob named '%s'", name.c_str());
   const Tensor& t = *tensors_[it->second];
+  if (t.elided && out)
+    fail(SIVO_EINVAL, "blob '%s' is not materialised in this build (a fused kernel consumes it); create the net with keep_blobs", name.c_str());
   if (n) *n = t.v.n;
   if (c) *c = t.v.c;
   if (h) *h = t.v.h;

@@ -22,10 +22,11 @@ struct Tensor {
   TensorView v;
   DevBuf buf;
   bool is_mask = false;  // u8 2-bit argmax codes, dims = pooled dims
+  bool elided = false;   // a fusion consumes this blob in registers: it is never written (blob() refuses to read it)
 };
 
 struct Op {
-  enum Kind { Input, LRN, Expand, InputPad8, Conv, Pool, Unpool, Dropout, Reduce } kind = Input;
+  enum Kind { Input, LRN, Expand, InputPad8, DropoutUnpool, Conv, Pool, Unpool, Dropout, Reduce } kind = Input;
   std::string layer;
   int in = -1, in2 = -1, out = -1, out2 = -1;
   // LRN
@@ -61,6 +62,9 @@ class SegNet {
   void blob(const std::string& name, float* out, size_t cap, int* n, int* c, int* h, int* w);
   void set_profiling(bool on) { profiling_ = on; }
   float conv_ms = 0, other_ms = 0, reduce_ms = 0, total_ms = 0;
+  std::vector<float> op_ms;  // per launch of the last profiled run, in launch order
+  size_t n_ops() const { return ops_.size(); }
+  const Op& op_at(size_t i) const { return ops_[i]; }
   int launches = 0;
   double flops_dedup = 0, flops_naive = 0;
 

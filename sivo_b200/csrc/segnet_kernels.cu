@@ -212,6 +212,55 @@ __global__ void k_dropout(const AT* __restrict__ in, int in_n, AT* __restrict__ 
   }
 }
 
+// half activations, channel count a multiple of 8: one thread per (sample, pixel, 8-channel chunk), 16-byte accesses.
+// y = x * 2 is exact in half, so this equals the generic kernel's float multiply + rounding.  With UNPOOL the result
+// is scattered straight into the 2x2 block its pooling mask names (dropout -> upsample pair of the decoder entry).
+template <bool UNPOOL>
+__global__ void k_dropout_h8(const uint4* __restrict__ in, int in_n, uint4* __restrict__ out, int N, int Hi, int Wi, int cs,
+                             uint64_t seed, const uint64_t* __restrict__ frame, int layer, float scale,
+                             const uint8_t* __restrict__ mask, int mask_n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int chunks = cs >> 3;
+  const int HW = Hi * Wi;
+  if (i >= static_cast<size_t>(N) * HW * chunks) return;
+  const int ch = static_cast<int>(i % chunks);
+  const size_t r = i / chunks;
+  const uint32_t pix = static_cast<uint32_t>(r % HW);
+  const int n = static_cast<int>(r / HW);
+  uint32_t bits[4];
+  dropout_bits128(seed, *frame, layer, n, pix, ch >> 4, bits);
+  const uint32_t b = (bits[(ch >> 2) & 3] >> ((ch & 3) * 8)) & 0xFFu;
+  const uint4 v = __ldg(in + (static_cast<size_t>(n % in_n) * HW + pix) * chunks + ch);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __half2 s2 = __floats2half2_rn((b >> (2 * k)) & 1u ? scale : 0.f, (b >> (2 * k + 1)) & 1u ? scale : 0.f);
+    const __half2 h = __hmul2(*reinterpret_cast<const __half2*>(&w[k]), s2);
+    o[k] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  if (!UNPOOL) {
+    out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    return;
+  }
+  const uint2 m = __ldg(reinterpret_cast<const uint2*>(mask + ((static_cast<size_t>(n % mask_n) * HW + pix) * cs + ch * 8)));
+  const uint32_t mw[2] = {m.x, m.y};
+  const int hi = pix / Wi, wi = pix % Wi;
+#pragma unroll
+  for (int pos = 0; pos < 4; ++pos) {
+    uint32_t sel[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t mb = mw[k >> 1] >> ((k & 1) * 16);
+      const uint32_t lo = ((mb & 0xFFu) == static_cast<uint32_t>(pos)) ? 0x0000FFFFu : 0u;
+      const uint32_t hi2 = (((mb >> 8) & 0xFFu) == static_cast<uint32_t>(pos)) ? 0xFFFF0000u : 0u;
+      sel[k] = o[k] & (lo | hi2);
+    }
+    out[((static_cast<size_t>(n) * 2 * Hi + 2 * hi + (pos >> 1)) * (2 * Wi) + 2 * wi + (pos & 1)) * chunks + ch] =
+        make_uint4(sel[0], sel[1], sel[2], sel[3]);
+  }
+}
+
 __global__ void k_dropout_bits(uint64_t seed, const uint64_t* frame, int layer, int T, int C, int HW,
                                uint8_t* __restrict__ keep) {
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -286,8 +335,16 @@ __global__ void k_mc_reduce_quad(const float* __restrict__ logits, int T, int C,
   const bool live = pix < hw;
   const int pp = live ? pix : hw - 1;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int t = 0; t < T; ++t) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(logits + (static_cast<size_t>(t) * hw + pp) * 16) + q);
+  constexpr int kBatch = 6;  // samples whose loads are issued together (memory-level parallelism: the pass is HBM-bound)
+  for (int t0 = 0; t0 < T; t0 += kBatch) {
+  float4 vb[kBatch];
+#pragma unroll
+  for (int b = 0; b < kBatch; ++b)
+    if (t0 + b < T) vb[b] = __ldcs(reinterpret_cast<const float4*>(logits + (static_cast<size_t>(t0 + b) * hw + pp) * 16) + q);
+#pragma unroll
+  for (int b = 0; b < kBatch; ++b) {
+    if (t0 + b >= T) break;
+    const float4 v = vb[b];
     float x[4] = {v.x, v.y, v.z, v.w};
     float m = -INFINITY;
 #pragma unroll
@@ -305,6 +362,7 @@ __global__ void k_mc_reduce_quad(const float* __restrict__ logits, int T, int C,
     const float inv = __frcp_rn(sum);
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[j] += static_cast<double>(__fmul_rn(x[j], inv));
+  }
   }
   const double inv_t = 1.0 / static_cast<double>(T);
   double best = -1.0, ent = 0.0;
@@ -581,11 +639,29 @@ void launch_unpool(TensorView in, const uint8_t* mask, int mask_n, TensorView ou
 }
 
 void launch_dropout(TensorView in, TensorView out, const DropoutParams& d, float scale, cudaStream_t s) {
+  if (in.dt == DType::F16 && out.dt == DType::F16 && out.cs % 8 == 0 && out.c == out.cs && in.cs == out.cs) {
+    const size_t total = static_cast<size_t>(out.n) * out.h * out.w * (out.cs / 8);
+    k_dropout_h8<false><<<blocks_for(total, 256), 256, 0, s>>>(static_cast<const uint4*>(in.p), in.n, static_cast<uint4*>(out.p), out.n,
+                                                            out.h, out.w, out.cs, d.seed, d.frame_dev, d.layer, scale, nullptr, 1);
+    SIVO_CUDA(cudaGetLastError());
+    return;
+  }
   int words = (out.cs + 31) / 32;
   size_t total = static_cast<size_t>(out.n) * out.h * out.w * words;
   DISPATCH_AT(in.dt, (k_dropout<AT><<<blocks_for(total, 256), 256, 0, s>>>(static_cast<const AT*>(in.p), in.n,
                                                                            static_cast<AT*>(out.p), out.n, out.h * out.w,
                                                                            out.cs, out.c, d.seed, d.frame_dev, d.layer, scale)));
+  SIVO_CUDA(cudaGetLastError());
+}
+
+void launch_dropout_unpool(TensorView in, int T, const uint8_t* mask, int mask_n, TensorView out, const DropoutParams& d, float scale,
+                           cudaStream_t s) {
+  if (in.dt != DType::F16 || out.dt != DType::F16 || in.cs % 8 || in.c != in.cs || out.cs != in.cs || out.h != 2 * in.h || out.w != 2 * in.w ||
+      out.n != T)
+    fail(SIVO_EINVAL, "dropout+unpool: unexpected tensor layout");
+  const size_t total = static_cast<size_t>(T) * in.h * in.w * (in.cs / 8);
+  k_dropout_h8<true><<<blocks_for(total, 256), 256, 0, s>>>(static_cast<const uint4*>(in.p), in.n, static_cast<uint4*>(out.p), T, in.h, in.w,
+                                                         in.cs, d.seed, d.frame_dev, d.layer, scale, mask, mask_n);
   SIVO_CUDA(cudaGetLastError());
 }
 

@@ -42,6 +42,8 @@ void launch_conv_simt(const ConvParams& p, cudaStream_t s);
 // 4-channel input -> K*blk-channel tap-expanded tensor (see k_expand_taps)
 void launch_expand_taps(TensorView in, TensorView out, int K, int blk, cudaStream_t s);
 // [N][H][W][4] half -> zero-padded [N][H][W + 8][8] half (3 zero pixels left, 5 right, channels 4..7 zero)
+void launch_dropout_unpool(TensorView in, int T, const uint8_t* mask, int mask_n, TensorView out, const DropoutParams& d, float scale,
+                           cudaStream_t s);
 void launch_pad8(TensorView in, TensorView out, cudaStream_t s);
 // the three steps input_u8 -> lrn -> pad8 in one pass (same arithmetic, so the same half values)
 void launch_input_lrn_pad8(const uint8_t* bgr, TensorView out, int size, float alpha, float beta, float k, cudaStream_t s);

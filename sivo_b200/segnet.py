@@ -85,6 +85,18 @@ class BayesianSegNet:
                                          None, None, None, None))
         return out
 
+    def op_timings(self):
+        """[(layer names, ms in the last profiled run, algorithmic conv flops)] per launch of the op list."""
+        n = C.c_int()
+        L.check(L.lib().sivo_segnet_op_timing(self._h, -1, None, 0, None, None, C.byref(n)))
+        out = []
+        for i in range(n.value):
+            buf = C.create_string_buffer(256)
+            ms, fl = C.c_float(), C.c_double()
+            L.check(L.lib().sivo_segnet_op_timing(self._h, i, buf, 256, C.byref(ms), C.byref(fl), None))
+            out.append((buf.value.decode(), ms.value, fl.value))
+        return out
+
     def last_timing(self):
         a, b, c, d, n = C.c_float(), C.c_float(), C.c_float(), C.c_float(), C.c_int()
         L.check(L.lib().sivo_segnet_last_timing(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(n)))

@@ -204,8 +204,12 @@ def test_fused_epilogues_equal_the_unfused_ops(model_dir):
         seg.set_frame(5)
         res.append(seg.segmentImage(left))
         # pooled activations, argmax masks and unpooled tensors exist in both builds; fused or not they are the same arithmetic
-        pooled.append({n: seg.blob(n) for n in ("pool1", "pool1_mask", "pool2", "pool2_mask", "pool3_mask", "pool4", "pool4_mask",
-                                                "upsample3", "upsample1")})
+        pooled.append({n: seg.blob(n) for n in ("pool1", "pool1_mask", "pool2", "pool2_mask", "pool3_mask", "pool4_mask",
+                                                "upsample4", "upsample3", "upsample1")})
+        if not keep:  # blobs a fused kernel consumes in registers are refused, not returned stale
+            for elided in ("conv1", "conv_decode1", "norm"):
+                with pytest.raises(Exception):
+                    seg.blob(elided)
     for n in pooled[0]:
         assert np.array_equal(pooled[0][n], pooled[1][n]), n
     (c0, f0, e0), (c1, f1, e1) = res
