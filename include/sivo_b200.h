@@ -86,6 +86,15 @@ int sivo_segnet_run_device(sivo_segnet_t* h, const uint8_t* bgr_device, uint8_t*
 int sivo_segnet_blob(sivo_segnet_t* h, const char* name, float* out, size_t cap, int* n, int* c, int* hh,
                      int* ww);
 /* Enables per-op CUDA-event timing (adds a host sync per run); off by default. */
+/* Frame::SelectSemanticKeys (Frame.cc:177-203) plus the per-keypoint reads of the three maps that Tracking / LocalMapping
+ * do later (Tracking.cc:487,538; LocalMapping.cc:483-485), evaluated on the device-resident maps of the last
+ * sivo_segnet_run / _run_device -- so a caller that only needs per-keypoint values can pass NULL maps to sivo_segnet_run
+ * and skip the 6.1 MB read-back.  For keypoint i: (row, col) = ((int) y, (int) x); kp_class/kp_conf/kp_entropy[i] = the map
+ * values there (class 255, 0, 0 and never kept if outside the maps -- the reference would read out of bounds).
+ * keep_idx[0..*n_keep) = indices with class <= max_static_class (Classes::TERRAIN = 8 in the reference), ascending, i.e. the
+ * order mvKeysSemantic / mDescriptorsSemantic are built in.  Any output pointer may be NULL. */
+int sivo_segnet_semantic_keys(sivo_segnet_t* h, const sivo_keypoint* kps, int n, int max_static_class, uint8_t* kp_class,
+                              double* kp_conf, double* kp_entropy, int* keep_idx, int* n_keep);
 int sivo_segnet_set_profiling(sivo_segnet_t* h, int on);
 /* Per-stage device times (ms) of the last run: conv, other layers, MC reduction, total; counts kernels. */
 int sivo_segnet_last_timing(const sivo_segnet_t* h, float* conv_ms, float* other_ms, float* reduce_ms,

@@ -608,3 +608,17 @@ def compute_stereo_matches(kl, dl, kr, dr, pyr_l, pyr_r, scale, inv_scale, mb, m
             u_right[il] = -1
             depth[il] = -1
     return u_right, depth
+
+
+def select_semantic_keys(kps_xy, classes, confidence=None, entropy=None, max_static_class=8):
+    """Frame::SelectSemanticKeys (Frame.cc:177-203): col = int(pt.x), row = int(pt.y) (C++ truncation), keep the keypoint
+    iff mClasses(row, col) <= Classes::TERRAIN (= 8, bayesian_segnet.hpp:67-83), in keypoint order.  Also returns the per-keypoint
+    reads of the maps (what Tracking.cc:487,538 / LocalMapping.cc:483-485 look up later).  kps_xy: [n, 2] float32 (x, y)."""
+    kps_xy = np.asarray(kps_xy, np.float32)
+    col = np.trunc(kps_xy[:, 0]).astype(np.int64)
+    row = np.trunc(kps_xy[:, 1]).astype(np.int64)
+    cls = classes[row, col]
+    keep = np.nonzero(cls <= max_static_class)[0].astype(np.int32)
+    conf = confidence[row, col] if confidence is not None else None
+    ent = entropy[row, col] if entropy is not None else None
+    return cls, conf, ent, keep

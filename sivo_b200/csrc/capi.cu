@@ -107,6 +107,14 @@ int sivo_segnet_last_timing(const sivo_segnet_t* h, float* conv_ms, float* other
   });
 }
 
+int sivo_segnet_semantic_keys(sivo_segnet_t* h, const sivo_keypoint* kps, int n, int max_static_class, uint8_t* kp_class, double* kp_conf,
+                              double* kp_entropy, int* keep_idx, int* n_keep) {
+  return guarded([&] {
+    if (!h) fail(SIVO_EINVAL, "null handle");
+    h->impl->semantic_keys(kps, n, max_static_class, kp_class, kp_conf, kp_entropy, keep_idx, n_keep);
+  });
+}
+
 int sivo_segnet_op_timing(const sivo_segnet_t* h, int index, char* name, size_t cap, float* ms, double* flops, int* n_ops) {
   return guarded([&] {
     if (!h) fail(SIVO_EINVAL, "null handle");

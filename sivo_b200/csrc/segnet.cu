@@ -456,9 +456,47 @@ void SegNet::enqueue(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_
   }
 }
 
+void SegNet::semantic_keys(const sivo_keypoint* kps, int n, int max_static_class, uint8_t* kp_class, double* kp_conf, double* kp_entropy,
+                           int* keep_idx, int* n_keep) {
+  if (n_keep) *n_keep = 0;
+  if (n < 0 || (n > 0 && !kps)) fail(SIVO_EINVAL, "semantic_keys: bad keypoint array");
+  if (!last_classes_ || !last_conf_ || !last_ent_) fail(SIVO_EINVAL, "semantic_keys: no segmentation result on the device yet (or a map pointer was NULL)");
+  if (n == 0) return;
+  SIVO_CUDA(cudaSetDevice(device_));
+  cudaStream_t s = last_stream_;
+  const size_t in_bytes = static_cast<size_t>(n) * sizeof(sivo_keypoint);
+  const size_t out_bytes = static_cast<size_t>(n) * 17;  // n doubles, n doubles, n bytes
+  if (d_kp_.bytes < in_bytes) d_kp_.alloc(in_bytes * 2);
+  if (d_kp_out_.bytes < out_bytes) d_kp_out_.alloc(out_bytes * 2);
+  h_kp_.ensure(in_bytes);
+  h_kp_out_.ensure(out_bytes);
+  memcpy(h_kp_.p, kps, in_bytes);
+  SIVO_CUDA(cudaMemcpyAsync(d_kp_.p, h_kp_.p, in_bytes, cudaMemcpyHostToDevice, s));
+  double* o_conf = d_kp_out_.as<double>();
+  double* o_ent = o_conf + n;
+  uint8_t* o_cls = reinterpret_cast<uint8_t*>(o_ent + n);
+  launch_keypoint_lookup(d_kp_.as<sivo_keypoint>(), n, last_classes_, last_conf_, last_ent_, H_, W_, o_cls, o_conf, o_ent, s);
+  SIVO_CUDA(cudaMemcpyAsync(h_kp_out_.p, d_kp_out_.p, out_bytes, cudaMemcpyDeviceToHost, s));
+  SIVO_CUDA(cudaStreamSynchronize(s));
+  const double* hc = h_kp_out_.as<double>();
+  const double* he = hc + n;
+  const uint8_t* hk = reinterpret_cast<const uint8_t*>(he + n);
+  if (kp_conf) memcpy(kp_conf, hc, static_cast<size_t>(n) * sizeof(double));
+  if (kp_entropy) memcpy(kp_entropy, he, static_cast<size_t>(n) * sizeof(double));
+  if (kp_class) memcpy(kp_class, hk, n);
+  int kept = 0;
+  for (int i = 0; i < n; ++i)
+    if (hk[i] != 255 && static_cast<int>(hk[i]) <= max_static_class) {  // `detection <= Classes::TERRAIN` (Frame.cc:190)
+      if (keep_idx) keep_idx[kept] = i;
+      ++kept;
+    }
+  if (n_keep) *n_keep = kept;
+}
+
 void SegNet::run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_dev, double* ent_dev, cudaStream_t s) {
   SIVO_CUDA(cudaSetDevice(device_));
   if (!s) s = stream_;
+  last_classes_ = classes_dev; last_conf_ = conf_dev; last_ent_ = ent_dev; last_stream_ = s;
   *h_frame_.as<uint64_t>() = frame_++;
   SIVO_CUDA(cudaMemcpyAsync(d_frame_.p, h_frame_.p, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
   if (profiling_) {

@@ -59,6 +59,8 @@ class SegNet {
   void set_frame(uint64_t f) { frame_ = f; }
   void run_host(const uint8_t* bgr, int rows, int cols, size_t stride, uint8_t* classes, double* conf, double* ent);
   void run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_dev, double* ent_dev, cudaStream_t s);
+  void semantic_keys(const sivo_keypoint* kps, int n, int max_static_class, uint8_t* kp_class, double* kp_conf, double* kp_entropy,
+                     int* keep_idx, int* n_keep);
   void blob(const std::string& name, float* out, size_t cap, int* n, int* c, int* h, int* w);
   void set_profiling(bool on) { profiling_ = on; }
   float conv_ms = 0, other_ms = 0, reduce_ms = 0, total_ms = 0;
@@ -86,6 +88,13 @@ class SegNet {
   cudaStream_t stream_ = nullptr;
   DevBuf d_bgr_, d_classes_, d_conf_, d_ent_, d_frame_;
   PinnedBuf h_in_, h_classes_, h_conf_, h_ent_, h_frame_;
+  // where the last run left its maps on the device, and the stream it ran on (semantic_keys reads them)
+  const uint8_t* last_classes_ = nullptr;
+  const double* last_conf_ = nullptr;
+  const double* last_ent_ = nullptr;
+  cudaStream_t last_stream_ = nullptr;
+  DevBuf d_kp_, d_kp_out_;
+  PinnedBuf h_kp_, h_kp_out_;
   std::vector<cudaEvent_t> events_;
   // the op list captured once as a CUDA graph (one launch per frame); re-captured if the buffers or the stream change
   cudaGraphExec_t graph_exec_ = nullptr;

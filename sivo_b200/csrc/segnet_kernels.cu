@@ -609,6 +609,26 @@ void launch_expand_taps(TensorView in, TensorView out, int K, int blk, cudaStrea
   SIVO_CUDA(cudaGetLastError());
 }
 
+__global__ void k_keypoint_lookup(const sivo_keypoint* __restrict__ kps, int n, const uint8_t* __restrict__ classes,
+                                  const double* __restrict__ conf, const double* __restrict__ ent, int H, int W,
+                                  uint8_t* __restrict__ out_class, double* __restrict__ out_conf, double* __restrict__ out_ent) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int col = static_cast<int>(kps[i].x), row = static_cast<int>(kps[i].y);  // static_cast<int>(pt.x / pt.y): truncation
+  const bool ok = col >= 0 && col < W && row >= 0 && row < H;
+  const size_t o = ok ? static_cast<size_t>(row) * W + col : 0;
+  out_class[i] = ok ? classes[o] : static_cast<uint8_t>(255);
+  out_conf[i] = ok ? conf[o] : 0.0;
+  out_ent[i] = ok ? ent[o] : 0.0;
+}
+
+void launch_keypoint_lookup(const sivo_keypoint* kps, int n, const uint8_t* classes, const double* conf, const double* ent, int H, int W,
+                            uint8_t* out_class, double* out_conf, double* out_ent, cudaStream_t s) {
+  if (n <= 0) return;
+  k_keypoint_lookup<<<blocks_for(n, 128), 128, 0, s>>>(kps, n, classes, conf, ent, H, W, out_class, out_conf, out_ent);
+  SIVO_CUDA(cudaGetLastError());
+}
+
 void launch_pad8(TensorView in, TensorView out, cudaStream_t s) {
   if (in.dt != DType::F16 || in.cs != 4 || out.cs != 8 || out.w != in.w + 8) fail(SIVO_EINVAL, "pad8: unexpected tensor layout");
   const size_t total = static_cast<size_t>(out.n) * out.h * out.w;

@@ -73,6 +73,33 @@ class BayesianSegNet:
                                         conf.ctypes.data_as(C.c_void_p), ent.ctypes.data_as(C.c_void_p)))
         return classes, conf, ent
 
+    def segment_on_device(self, image: np.ndarray):
+        """segmentImage without the read-back: the three maps stay on the device for semantic_keys()."""
+        if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
+            raise ValueError("segmentImage expects an HxWx3 uint8 BGR image")
+        if image.strides[2] != 1 or image.strides[1] != 3:
+            image = np.ascontiguousarray(image)
+        L.check(L.lib().sivo_segnet_run(self._h, image.ctypes.data_as(C.c_void_p), image.shape[0], image.shape[1],
+                                        C.c_size_t(image.strides[0]), None, None, None))
+
+    def semantic_keys(self, kps: np.ndarray, max_static_class: int = 8):
+        """Frame::SelectSemanticKeys (Frame.cc:177-203) + per-keypoint map reads on the device-resident result of the last
+        run.  kps: structured array (orb.KP_DTYPE).  Returns (classes u8 [n], confidence f64 [n], entropy f64 [n], keep int32 [m]):
+        keep = indices whose class <= max_static_class (Classes::TERRAIN), in keypoint order."""
+        kps = np.ascontiguousarray(kps)
+        if kps.dtype.itemsize != 28:
+            raise ValueError("keypoints must be the 28-byte sivo_keypoint records")
+        n = len(kps)
+        cls = np.empty(n, np.uint8)
+        conf = np.empty(n, np.float64)
+        ent = np.empty(n, np.float64)
+        keep = np.empty(max(n, 1), np.int32)
+        m = C.c_int(0)
+        L.check(L.lib().sivo_segnet_semantic_keys(self._h, kps.ctypes.data_as(C.c_void_p), n, int(max_static_class),
+                                                  cls.ctypes.data_as(C.c_void_p), conf.ctypes.data_as(C.c_void_p),
+                                                  ent.ctypes.data_as(C.c_void_p), keep.ctypes.data_as(C.c_void_p), C.byref(m)))
+        return cls, conf, ent, keep[:m.value].copy()
+
     def run_device(self, bgr_ptr: int, classes_ptr: int, conf_ptr: int, ent_ptr: int, stream: int = 0):
         L.check(L.lib().sivo_segnet_run_device(self._h, C.c_void_p(bgr_ptr), C.c_void_p(classes_ptr), C.c_void_p(conf_ptr),
                                                C.c_void_p(ent_ptr), C.c_void_p(stream)))

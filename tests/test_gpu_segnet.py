@@ -216,3 +216,36 @@ def test_fused_epilogues_equal_the_unfused_ops(model_dir):
     assert (c0 != c1).mean() < 1e-4
     assert np.abs(e0 - e1).max() < 1e-2 and np.median(np.abs(e0 - e1)) < 1e-9
     assert np.abs(f0 - f1).max() < 1e-2
+
+
+def test_semantic_keys_match_the_oracle_on_device_resident_maps(model_dir):
+    """Next-row 8(f)-2: SelectSemanticKeys + per-keypoint map reads evaluated on the device (bit-exact: pure indexing),
+    both after a normal segmentImage and after the no-read-back call."""
+    from oracle import orb_oracle as O
+    from sivo_b200 import ORBextractor
+    net, w, proto, model = _full_model(model_dir)
+    from sivo_b200.synth import bgr_to_gray
+    left, _ = stereo_frame(3)
+    seg = BayesianSegNet(BayesianSegNetParams(proto, model), seed=7, T=2, precision="fp16", engine="auto")
+    seg.set_frame(9)
+    classes, conf, ent = seg.segmentImage(left)
+    # the extractor sees the same crop the network does (resizeImage, bayesian_segnet.cpp:142-162)
+    y0, x0 = left.shape[0] // 2 - seg.height // 2, left.shape[1] // 2 - seg.width // 2
+    g = np.ascontiguousarray(bgr_to_gray(left)[y0:y0 + seg.height, x0:x0 + seg.width])
+    kps, _ = ORBextractor(1000, 1.2, 8, 20, 7)(g, None)
+    assert len(kps) > 500
+    xy = np.stack([kps["x"], kps["y"]], 1)
+    want = O.select_semantic_keys(xy, classes, conf, ent)
+    for attempt in range(2):
+        got = seg.semantic_keys(kps)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+        assert np.array_equal(got[3], want[3])
+        seg.set_frame(9)
+        seg.segment_on_device(left)  # same frame counter -> same dropout masks -> same maps, left on the device
+    # out-of-map keypoints: class 255, never kept; an empty list is fine
+    bad = kps[:3].copy()
+    bad["x"][0] = -5.0
+    bad["y"][1] = 1e6
+    c, _, _, keep = seg.semantic_keys(bad)
+    assert c[0] == 255 and c[1] == 255 and 0 not in keep and 1 not in keep
+    assert len(seg.semantic_keys(kps[:0])[3]) == 0

@@ -128,3 +128,21 @@ def test_hamming_distance():
         v = (v & 0x33333333) + ((v >> 2) & 0x33333333)
         d += ((((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) & 0xFFFFFFFF) >> 24
     assert d == O.descriptor_distance(a, b)
+
+
+def test_select_semantic_keys_is_the_reference_loop():
+    """Frame::SelectSemanticKeys (Frame.cc:177-203) as the literal loop: truncate pt to (row, col), keep iff class <= TERRAIN."""
+    rng = np.random.default_rng(5)
+    classes = rng.integers(0, 14, size=(40, 64)).astype(np.uint8)
+    classes[rng.random(classes.shape) < 0.05] = 255  # VOID
+    conf = rng.random(classes.shape)
+    ent = rng.random(classes.shape)
+    xy = np.stack([rng.uniform(0, 63.99, 300), rng.uniform(0, 39.99, 300)], 1).astype(np.float32)
+    cls, c, e, keep = O.select_semantic_keys(xy, classes, conf, ent)
+    want_keep = []
+    for i, (x, y) in enumerate(xy):
+        col, row = int(x), int(y)
+        assert cls[i] == classes[row, col] and c[i] == conf[row, col] and e[i] == ent[row, col]
+        if classes[row, col] <= 8:
+            want_keep.append(i)
+    assert keep.tolist() == want_keep
