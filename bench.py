@@ -185,7 +185,9 @@ def workload_config(args, T):
     return {"workload": f"Bayesian SegNet {args.model.capitalize()} T={T} + ORB({args.nfeatures}) x2, synthetic 1242x375 stereo "
                         f"(centre-cropped to 1024x352), one frame per GPU",
             "model": args.model, "T": T, "nfeatures": args.nfeatures, "engine": args.engine, "precision": args.precision,
-            "l2": "inputs+activations per frame (>300 MB) exceed the 126 MB L2; distinct frame each step"}
+            "l2": "inputs+activations per frame (>300 MB) exceed the 126 MB L2; distinct frame each step",
+            "calls": "per frame: segmentImage + the two ORBextractor calls, issued concurrently from three host threads "
+                     "(value: run_device graph replay + two run_device_input threads)"}
 
 
 def main():
