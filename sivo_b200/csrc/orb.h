@@ -45,7 +45,7 @@ struct OrbSelected {  // one retained keypoint, level coordinates
 // ---- kernels (orb_kernels.cu)
 void orb_launch_pyramid(const uint8_t* gray, int rows, int cols, size_t gray_pitch, uint8_t* pyr, const OrbLevelTable& t,
                         cudaStream_t s);
-void orb_launch_score(const uint8_t* pyr, uint8_t* score, const OrbLevelTable& t, cudaStream_t s);
+void orb_launch_score(const uint8_t* pyr, uint8_t* score, const OrbLevelTable& t, int t_min, cudaStream_t s);
 void orb_launch_cells(const uint8_t* score, const OrbLevelTable& t, const OrbCell* cells, int ncells, int ini_th, int min_th,
                       int* cell_count, uint32_t* cell_items, cudaStream_t s);
 void orb_launch_compact(const OrbLevelTable& t, const OrbCell* cells, int ncells, const int* cell_count,

@@ -425,7 +425,7 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
     SIVO_CUDA(cudaEventRecord(ev_[0], s));
   }
   orb_launch_pyramid(src, rows, cols, src_pitch, d_pyr_.as<uint8_t>(), lt_, s);
-  orb_launch_score(d_pyr_.as<uint8_t>(), d_score_.as<uint8_t>(), lt_, s);
+  orb_launch_score(d_pyr_.as<uint8_t>(), d_score_.as<uint8_t>(), lt_, std::min(ini_th_, min_th_), s);
   orb_launch_cells(d_score_.as<uint8_t>(), lt_, d_cells_.as<OrbCell>(), ncells, ini_th_, min_th_, d_cell_count_.as<int>(),
                    d_cell_items_.as<uint32_t>(), s);
   orb_launch_compact(lt_, d_cells_.as<OrbCell>(), ncells, d_cell_count_.as<int>(), d_cell_items_.as<uint32_t>(),

@@ -63,7 +63,10 @@ __global__ void k_resize(uint8_t* __restrict__ pyr, OrbLevel src, OrbLevel dst) 
 // ---- FAST-9/16 corner score (cv::FAST's cornerScore<16>): S = max over the 16 contiguous 9-arcs of
 // min(+-(ring - p)) - 1; p is a corner at threshold t iff S >= t.  One thread per pixel, all levels in
 // one launch (grid.y = level).  Only [19, w-19) x [19, h-19) can ever be a keypoint (cell interiors).
-__global__ void k_fast_score(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score, OrbLevelTable t) {
+// `t_min` = the smallest threshold any consumer applies (min(iniThFAST, minThFAST)): a 9-arc covers at least two of the four
+// compass points, so a pixel with fewer than two compass points brighter than p + t_min and fewer than two darker than
+// p - t_min has S < t_min, is zeroed by every threshold, and gets 0 without the full score (most pixels).
+__global__ void k_fast_score(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score, OrbLevelTable t, int t_min) {
   const OrbLevel lv = t.lv[blockIdx.y];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= lv.w * lv.h) return;
@@ -75,6 +78,16 @@ __global__ void k_fast_score(const uint8_t* __restrict__ pyr, uint8_t* __restric
     const int off[16] = {3 * P,      3 * P + 1,  2 * P + 2,  P + 3,  3,  -P + 3,  -2 * P + 2, -3 * P + 1,
                          -3 * P,     -3 * P - 1, -2 * P - 2, -P - 3, -3, P - 3,   2 * P - 2,  3 * P - 1};
     int v = c[0];
+    {
+      const int q[4] = {static_cast<int>(c[3 * P]) - v, static_cast<int>(c[3]) - v, static_cast<int>(c[-3 * P]) - v, static_cast<int>(c[-3]) - v};
+      int nb = 0, nd = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { nb += q[k] > t_min; nd += q[k] < -t_min; }
+      if (nb < 2 && nd < 2) {
+        score[lv.flat_off + i] = 0;
+        return;
+      }
+    }
     int d[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) d[k] = static_cast<int>(c[off[k]]) - v;
@@ -226,23 +239,35 @@ __global__ void k_gather_cells(const int* __restrict__ cell_count, const int* __
 // exact integer accumulation over both passes, one final rounding (v + 2^15) >> 16.  The 19-px reflected
 // border of the pyramid buffer supplies the 3-px halo.  Output is the borderless w*h plane the reference
 // blurs (`mvImagePyramid[level].clone()`, ORBextractor.cc:1060-1062).
+// One thread = four horizontally adjacent pixels: 10 bytes per source row serve four 7-tap row sums.
 __global__ void k_blur(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, OrbLevelTable t) {
   const OrbLevel lv = t.lv[blockIdx.y];
+  const int wq = (lv.w + 3) >> 2;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= lv.w * lv.h) return;
-  int x = i % lv.w, y = i / lv.w;
+  if (i >= wq * lv.h) return;
+  const int x = (i % wq) * 4, y = i / wq;
   const int g[7] = {18, 34, 48, 56, 48, 34, 18};
+  // columns x-3 .. x+6 exist in the bordered buffer for every x < w (19-px border), also for the ragged last quad
   const uint8_t* c = pyr + lv.img_off + static_cast<size_t>(y + kEdge - 3) * lv.pitch + x + kEdge - 3;
-  unsigned acc = 0;
+  unsigned acc[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int ky = 0; ky < 7; ++ky) {
-    unsigned r = 0;
+    unsigned v[10];
 #pragma unroll
-    for (int kx = 0; kx < 7; ++kx) r += g[kx] * c[kx];
-    acc += g[ky] * r;
+    for (int k = 0; k < 10; ++k) v[k] = c[k];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      unsigned r = 0;
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) r += g[kx] * v[o + kx];
+      acc[o] += g[ky] * r;
+    }
     c += lv.pitch;
   }
-  blur[lv.flat_off + i] = static_cast<uint8_t>((acc + 32768u) >> 16);
+  uint8_t* d = blur + lv.flat_off + static_cast<size_t>(y) * lv.w + x;
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+    if (x + o < lv.w) d[o] = static_cast<uint8_t>((acc[o] + 32768u) >> 16);
 }
 
 // ---- cv::fastAtan2 (degrees): 7th-order odd polynomial in float32 without FMA contraction.
@@ -336,9 +361,9 @@ void orb_launch_pyramid(const uint8_t* gray, int rows, int cols, size_t gray_pit
   SIVO_CUDA(cudaGetLastError());
 }
 
-void orb_launch_score(const uint8_t* pyr, uint8_t* score, const OrbLevelTable& t, cudaStream_t s) {
+void orb_launch_score(const uint8_t* pyr, uint8_t* score, const OrbLevelTable& t, int t_min, cudaStream_t s) {
   dim3 grid(ceil_div(t.lv[0].w * t.lv[0].h, 128), t.nlevels);
-  k_fast_score<<<grid, 128, 0, s>>>(pyr, score, t);
+  k_fast_score<<<grid, 128, 0, s>>>(pyr, score, t, t_min);
   SIVO_CUDA(cudaGetLastError());
 }
 
@@ -360,7 +385,7 @@ void orb_launch_compact(const OrbLevelTable& t, const OrbCell* cells, int ncells
 }
 
 void orb_launch_blur(const uint8_t* pyr, uint8_t* blur, const OrbLevelTable& t, cudaStream_t s) {
-  dim3 grid(ceil_div(t.lv[0].w * t.lv[0].h, 128), t.nlevels);
+  dim3 grid(ceil_div(((t.lv[0].w + 3) / 4) * t.lv[0].h, 128), t.nlevels);
   k_blur<<<grid, 128, 0, s>>>(pyr, blur, t);
   SIVO_CUDA(cudaGetLastError());
 }
