@@ -249,3 +249,26 @@ def test_semantic_keys_match_the_oracle_on_device_resident_maps(model_dir):
     c, _, _, keep = seg.semantic_keys(bad)
     assert c[0] == 255 and c[1] == 255 and 0 not in keep and 1 not in keep
     assert len(seg.semantic_keys(kps[:0])[3]) == 0
+
+
+def test_bn_absorbed_model_runs_and_agrees(tmp_path):
+    """8(f)-3: the model BN-absorber.py would write (BN folded into the convolutions, BN layers dropped) goes through the same
+    tensor-core path and gives the same segmentation as the BN form up to the half rounding of W * gamma."""
+    from sivo_b200 import bn_absorb
+    from sivo_b200.caffemodel import write_caffemodel
+    from sivo_b200.prototxt import load_net
+    net, w, proto, model = make_model(tmp_path, "standard", T=3, H=64, W=128, widths=(64, 64, 64, 64, 64))
+    new_text, new_w = bn_absorb.absorb(open(proto).read(), w)
+    p2, m2 = str(tmp_path / "merged.prototxt"), str(tmp_path / "merged.caffemodel")
+    open(p2, "w").write(new_text)
+    types = {l.name: l.type for l in net.layers}
+    write_caffemodel(m2, net.name, new_w, {k: types[k] for k in new_w})
+    left, _ = stereo_frame(4, w=128, h=64)
+    outs = []
+    for pr, mo in ((proto, model), (p2, m2)):
+        seg = BayesianSegNet(BayesianSegNetParams(pr, mo), seed=11, precision="fp16", engine="auto")
+        seg.set_frame(2)
+        outs.append(seg.segmentImage(left))
+    (c0, f0, e0), (c1, f1, e1) = outs
+    assert (c0 != c1).mean() < 0.02
+    assert np.median(np.abs(e0 - e1)) < 5e-3 and np.median(np.abs(f0 - f1)) < 5e-3

@@ -124,3 +124,42 @@ def test_quad_tree_matches_oracle():
         b = distribute_octtree(xs, ys, rs, 16, 16 + w, 16, 16 + h, tgt)
         assert list(a) == b.tolist()
         assert len(b) <= max(tgt + 3, 1) or len(b) <= n
+
+
+def test_bn_absorber_follows_the_reference_script(tmp_path):
+    """8(f)-3: BN-absorber.py restated (W' = W * gamma, b' = b * gamma + beta in float64, BN blobs zeroed, BN layers dropped);
+    the merged net computes the same probabilities as the BN net (fp32 rounding of W * gamma only), and the tool's files load."""
+    import torch
+    from conftest import make_model
+    from oracle import segnet_oracle as S
+    from sivo_b200 import bn_absorb
+    from sivo_b200.caffemodel import read_caffemodel
+    from sivo_b200.prototxt import load_net
+    from sivo_b200.synth import stereo_frame
+    net, w, proto, model = make_model(tmp_path, "standard", T=2, H=32, W=64, widths=(8, 8, 16, 16, 16))
+    text = open(proto).read()
+    new_text, new_w = bn_absorb.absorb(text, w)
+    bn_names = [l.name for l in net.layers if l.type == "BN"]
+    assert bn_names and all(n not in [l.name for l in load_net(new_text).layers] for n in bn_names)
+    assert len(load_net(new_text).layers) == len(net.layers) - len(bn_names)
+    # the literal per-feature-map loop of the script (:78-84)
+    for i, layer in enumerate(net.layers):
+        if layer.type != "BN":
+            continue
+        conv = net.layers[i - 1].name
+        weight = np.array(w[conv][0], dtype=np.double)
+        bias = np.array(w[conv][1], dtype=np.double).reshape(-1)
+        gamma, beta = w[layer.name][0].reshape(-1), w[layer.name][1].reshape(-1)
+        for j in range(weight.shape[0]):
+            assert np.array_equal(new_w[conv][0][j], (weight[j] * gamma.item(j)).astype(np.float32))
+            assert new_w[conv][1].reshape(-1)[j] == np.float32(bias[j] * gamma.item(j) + beta.item(j))
+        assert not new_w[layer.name][0].any() and not new_w[layer.name][1].any()
+    left, _ = stereo_frame(1, w=64, h=32)
+    p0 = S.forward(net, w, left, seed=3, frame=0)
+    p1 = S.forward(load_net(new_text), new_w, left, seed=3, frame=0)
+    assert np.abs(p0 - p1).max() < 2e-4
+    # command-line form writes the two files the script writes, and they read back
+    bn_absorb.main(["--model", proto, "--weights", model, "--out_dir", str(tmp_path / "merged")])
+    back = read_caffemodel(str(tmp_path / "merged" / "bn_conv_merged_weights.caffemodel"))
+    assert all(np.array_equal(back[k][0], new_w[k][0]) for k in new_w)
+    assert open(tmp_path / "merged" / "bn_conv_merged_model.prototxt").read() == new_text
