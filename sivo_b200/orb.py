@@ -30,8 +30,11 @@ class ORBextractor:
         self._scale_factor = scaleFactor
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            L.lib().sivo_orb_destroy(self._h)
+        if getattr(self, "_h", None) and self._h.value and L is not None and getattr(L, "lib", None):
+            try:
+                L.lib().sivo_orb_destroy(self._h)
+            except Exception:  # interpreter shutdown: module globals may already be gone
+                pass
             self._h = C.c_void_p()
 
     def GetLevels(self): return self.nlevels

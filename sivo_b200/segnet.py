@@ -38,8 +38,11 @@ class BayesianSegNet:
         self.width, self.height, self.T, self.n_classes = w.value, h.value, t.value, nc.value
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            L.lib().sivo_segnet_destroy(self._h)
+        if getattr(self, "_h", None) and self._h.value and L is not None and getattr(L, "lib", None):
+            try:
+                L.lib().sivo_segnet_destroy(self._h)
+            except Exception:  # interpreter shutdown: module globals may already be gone
+                pass
             self._h = C.c_void_p()
 
     def getInputGeometry(self):

@@ -1,4 +1,5 @@
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for i in 1 2; do timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2>/tmp/err.log | tail -1 | python -c "
-import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['orb_last_call'], d['roofline']['segnet_ms_per_frame'])"; done
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1h.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/b.log 2>&1
+for v in 1 0 1 0; do SIVO_B200_PDL=$v timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2>/tmp/err.log | tail -1 | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print('PDL=$v', d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['segnet_ms_per_frame'])"; done
+SIVO_B200_PDL=1 timeout 100 python tools/e2e_breakdown.py 2>&1 | grep "ms / frame"
+SIVO_B200_PDL=0 timeout 100 python tools/e2e_breakdown.py 2>&1 | grep "ms / frame"
