@@ -153,6 +153,17 @@ int sivo_stereo_match(const sivo_orb_t* left, const sivo_orb_t* right, const siv
                       int n_left, const sivo_keypoint* kp_right, const uint8_t* desc_right, int n_right, float mb, float mbf,
                       float* u_right, float* depth);
 
+/* Best / second-best match over per-query candidate lists -- the inner loop of ORBmatcher::SearchByProjection
+ * (ORBmatcher.cc:79-113), its last-frame / keyframe variants (:1278-, :1420-), SearchForTriangulation (:631-) and
+ * SearchBySim3 (next row 4).  Query i's candidates are cand_idx[cand_offsets[i] .. cand_offsets[i+1]) (indices into the
+ * train descriptors, in the order GetFeaturesInArea returned them; the caller has already dropped the ones its own
+ * state excludes).  out5[5 i ..] = {bestIdx, bestDist, bestLevel, bestDist2, bestLevel2} exactly as the sequential loop
+ * leaves them (strict '<', so the first minimum wins; 256 / -1 when there is no candidate).  train_level (octave per train
+ * keypoint) may be NULL (levels reported as 0).  The TH_HIGH / mfNNratio / orientation-histogram decisions stay with the
+ * caller, as does the in-loop `F.mvpMapPoints[bestIdx] = pMP` dependency between queries. */
+int sivo_hamming_best2(int device, const uint8_t* query_desc, int n_query, const uint8_t* train_desc, int n_train,
+                       const int* cand_offsets, const int* cand_idx, const int* train_level, int* out5);
+
 /* ---- test hooks for single layers (float NCHW host arrays in/out; run the product kernels) ----- */
 int sivo_dbg_pool(int device, const float* in, int n, int c, int h, int w, float* out, int* mask);
 int sivo_dbg_unpool(int device, const float* in, const int* mask, int n, int c, int h, int w, float* out);

@@ -622,3 +622,25 @@ def select_semantic_keys(kps_xy, classes, confidence=None, entropy=None, max_sta
     conf = confidence[row, col] if confidence is not None else None
     ent = entropy[row, col] if entropy is not None else None
     return cls, conf, ent, keep
+
+
+def hamming_best2(query_desc, train_desc, cand_offsets, cand_idx, train_level=None):
+    """The candidate loop of ORBmatcher::SearchByProjection (ORBmatcher.cc:79-113; the same loop body recurs at :1278-, :1420-,
+    :631-) as written: strict '<' on both tests, levels carried with the distances.  DescriptorDistance (:1582-1596) is the
+    popcount of the XOR of the two 256-bit descriptors.  Returns int32 [n_query, 5] = bestIdx, bestDist, bestLevel, bestDist2,
+    bestLevel2 (256 / -1 defaults)."""
+    q = np.asarray(query_desc, np.uint8).reshape(-1, 32)
+    t = np.asarray(train_desc, np.uint8).reshape(-1, 32)
+    out = np.empty((len(q), 5), np.int32)
+    for i in range(len(q)):
+        best_dist, best_level, best_dist2, best_level2, best_idx = 256, -1, 256, -1, -1
+        for idx in cand_idx[cand_offsets[i]:cand_offsets[i + 1]]:
+            dist = int(np.unpackbits(q[i] ^ t[idx]).sum())
+            lvl = 0 if train_level is None else int(train_level[idx])
+            if dist < best_dist:
+                best_dist2, best_level2 = best_dist, best_level
+                best_dist, best_level, best_idx = dist, lvl, int(idx)
+            elif dist < best_dist2:
+                best_level2, best_dist2 = lvl, dist
+        out[i] = (best_idx, best_dist, best_level, best_dist2, best_level2)
+    return out

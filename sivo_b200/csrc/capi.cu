@@ -237,6 +237,15 @@ int sivo_stereo_hamming(int device, const sivo_keypoint* left, const uint8_t* de
   });
 }
 
+int sivo_hamming_best2(int device, const uint8_t* query_desc, int n_query, const uint8_t* train_desc, int n_train,
+                       const int* cand_offsets, const int* cand_idx, const int* train_level, int* out5) {
+  return guarded([&] {
+    if (!out5 || !cand_offsets || (n_query && !query_desc) || (n_train && !train_desc) || (n_query > 0 && cand_offsets[n_query] && !cand_idx))
+      fail(SIVO_EINVAL, "null argument");
+    hamming_best2(device, query_desc, n_query, train_desc, n_train, cand_offsets, cand_idx, train_level, out5);
+  });
+}
+
 int sivo_stereo_match(const sivo_orb_t* left, const sivo_orb_t* right, const sivo_keypoint* kp_left, const uint8_t* desc_left,
                       int n_left, const sivo_keypoint* kp_right, const uint8_t* desc_right, int n_right, float mb, float mbf,
                       float* u_right, float* depth) {

@@ -172,6 +172,68 @@ void stereo_hamming(int device, const sivo_keypoint* left, const uint8_t* dl, in
   SIVO_CUDA(cudaMemcpy(best_dist, d_bd.p, nl * sizeof(int), cudaMemcpyDeviceToHost));
 }
 
+// ---- best / second-best descriptor match over per-query candidate lists: the inner loop shared by
+// ORBmatcher::SearchByProjection (ORBmatcher.cc:79-113 and :1278-), SearchForTriangulation (:631-) and SearchBySim3 --
+//   bestDist = bestDist2 = 256, bestLevel = bestLevel2 = -1, bestIdx = -1;
+//   for idx in candidates (in order): dist = DescriptorDistance(q, train[idx]);
+//     if (dist < bestDist) { bestDist2 = bestDist; bestLevel2 = bestLevel; bestDist = dist; bestLevel = level[idx]; bestIdx = idx; }
+//     else if (dist < bestDist2) { bestLevel2 = level[idx]; bestDist2 = dist; }
+// One warp per query: the lanes compute 32 distances at a time, lane 0 folds them in candidate order so that ties fall
+// exactly as in the sequential loop.
+namespace {
+__global__ void k_hamming_best2(const uint8_t* __restrict__ query, int nq, const uint8_t* __restrict__ train,
+                                const int* __restrict__ cand_off, const int* __restrict__ cand_idx, const int* __restrict__ level,
+                                int* __restrict__ out) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= nq) return;
+  const ulonglong4 a = *reinterpret_cast<const ulonglong4*>(query + static_cast<size_t>(wid) * 32);
+  const int b = cand_off[wid], e = cand_off[wid + 1];
+  int best_dist = 256, best_level = -1, best_dist2 = 256, best_level2 = -1, best_idx = -1;
+  for (int base = b; base < e; base += 32) {
+    const int i = base + lane;
+    int d = 0x7FFFFFFF, idx = -1, lvl = -1;
+    if (i < e) {
+      idx = cand_idx[i];
+      const ulonglong4 t = *reinterpret_cast<const ulonglong4*>(train + static_cast<size_t>(idx) * 32);
+      d = __popcll(a.x ^ t.x) + __popcll(a.y ^ t.y) + __popcll(a.z ^ t.z) + __popcll(a.w ^ t.w);
+      lvl = level ? level[idx] : 0;
+    }
+    const int n = min(32, e - base);
+    for (int k = 0; k < n; ++k) {  // warp-uniform fold in candidate order
+      const int dk = __shfl_sync(0xffffffffu, d, k), ik = __shfl_sync(0xffffffffu, idx, k), lk = __shfl_sync(0xffffffffu, lvl, k);
+      if (dk < best_dist) { best_dist2 = best_dist; best_level2 = best_level; best_dist = dk; best_level = lk; best_idx = ik; }
+      else if (dk < best_dist2) { best_level2 = lk; best_dist2 = dk; }
+    }
+  }
+  if (lane == 0) {
+    int* o = out + static_cast<size_t>(wid) * 5;
+    o[0] = best_idx; o[1] = best_dist; o[2] = best_level; o[3] = best_dist2; o[4] = best_level2;
+  }
+}
+}  // namespace
+
+void hamming_best2(int device, const uint8_t* query, int nq, const uint8_t* train, int nt, const int* cand_off, const int* cand_idx,
+                   const int* train_level, int* out5) {
+  if (nq < 0 || nt < 0) fail(SIVO_EINVAL, "hamming_best2: negative counts");
+  if (nq == 0) return;
+  if (cand_off[0] != 0) fail(SIVO_EINVAL, "hamming_best2: candidate offsets must start at 0");
+  for (int i = 0; i < nq; ++i) if (cand_off[i + 1] < cand_off[i]) fail(SIVO_EINVAL, "hamming_best2: candidate offsets must not decrease");
+  const int nc = cand_off[nq];
+  for (int i = 0; i < nc; ++i) if (cand_idx[i] < 0 || cand_idx[i] >= nt) fail(SIVO_ERANGE, "hamming_best2: candidate %d names train descriptor %d of %d", i, cand_idx[i], nt);
+  SIVO_CUDA(cudaSetDevice(device));
+  DevBuf d_q(static_cast<size_t>(nq) * 32), d_t(static_cast<size_t>(std::max(nt, 1)) * 32), d_off((nq + 1) * sizeof(int)),
+      d_idx(std::max(nc, 1) * sizeof(int)), d_lvl(std::max(nt, 1) * sizeof(int)), d_out(static_cast<size_t>(nq) * 5 * sizeof(int));
+  SIVO_CUDA(cudaMemcpy(d_q.p, query, static_cast<size_t>(nq) * 32, cudaMemcpyHostToDevice));
+  if (nt) SIVO_CUDA(cudaMemcpy(d_t.p, train, static_cast<size_t>(nt) * 32, cudaMemcpyHostToDevice));
+  SIVO_CUDA(cudaMemcpy(d_off.p, cand_off, (nq + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  if (nc) SIVO_CUDA(cudaMemcpy(d_idx.p, cand_idx, nc * sizeof(int), cudaMemcpyHostToDevice));
+  if (train_level && nt) SIVO_CUDA(cudaMemcpy(d_lvl.p, train_level, nt * sizeof(int), cudaMemcpyHostToDevice));
+  k_hamming_best2<<<ceil_div(nq * 32, 128), 128>>>(d_q.as<uint8_t>(), nq, d_t.as<uint8_t>(), d_off.as<int>(), d_idx.as<int>(),
+                                                   train_level ? d_lvl.as<int>() : nullptr, d_out.as<int>());
+  SIVO_CUDA(cudaGetLastError());
+  SIVO_CUDA(cudaMemcpy(out5, d_out.p, static_cast<size_t>(nq) * 5 * sizeof(int), cudaMemcpyDeviceToHost));
+}
+
 }  // namespace sivo
 
 namespace sivo {

@@ -154,3 +154,20 @@ def stereo_match(left: ORBextractor, right: ORBextractor, kp_left, desc_left, kp
                                       kr.ctypes.data_as(C.c_void_p), dr.ctypes.data_as(C.c_void_p), len(kr), C.c_float(mb),
                                       C.c_float(mbf), u.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p)))
     return u, z
+
+
+def hamming_best2(query_desc, train_desc, cand_offsets, cand_idx, train_level=None, device: int = 0) -> np.ndarray:
+    """Inner loop of ORBmatcher::SearchByProjection & co (ORBmatcher.cc:79-113) for all queries at once.
+    Returns int32 [n_query, 5] = (bestIdx, bestDist, bestLevel, bestDist2, bestLevel2)."""
+    q = np.ascontiguousarray(query_desc, np.uint8).reshape(-1, 32)
+    t = np.ascontiguousarray(train_desc, np.uint8).reshape(-1, 32)
+    off = np.ascontiguousarray(cand_offsets, np.int32)
+    idx = np.ascontiguousarray(cand_idx, np.int32)
+    if len(off) != len(q) + 1:
+        raise ValueError("cand_offsets must have n_query + 1 entries")
+    lvl = None if train_level is None else np.ascontiguousarray(train_level, np.int32)
+    out = np.empty((len(q), 5), np.int32)
+    L.check(L.lib().sivo_hamming_best2(device, q.ctypes.data_as(C.c_void_p), len(q), t.ctypes.data_as(C.c_void_p), len(t),
+                                       off.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p),
+                                       None if lvl is None else lvl.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+    return out

@@ -137,3 +137,34 @@ def test_stereo_match_full_vs_oracle():
     ru, rz = O.compute_stereo_matches(kl, dl, kr, dr, el._bordered, er._bordered, el.GetScaleFactors(), el.GetInverseScaleFactors(), mb, mbf)
     assert np.array_equal(u, ru) and np.array_equal(z, rz)
     assert (u >= 0).sum() > 150
+
+
+def test_hamming_best2_equals_the_sequential_loop():
+    """Next row 8(f)-4: best / second-best over candidate lists, ties and empty lists included (bit-exact: integers)."""
+    from sivo_b200.orb import hamming_best2
+    rng = np.random.default_rng(11)
+    nt, nq = 700, 400
+    train = rng.integers(0, 256, size=(nt, 32), dtype=np.uint8)
+    # queries near some train descriptors (a few bits flipped) so that small distances and exact ties occur
+    src = rng.integers(0, nt, nq)
+    query = train[src].copy()
+    for i in range(nq):
+        flips = rng.integers(0, 256, size=rng.integers(0, 40))
+        for b in flips:
+            query[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    train[5] = train[9]  # duplicated descriptors: equal distances inside one list
+    train[17] = train[9]
+    level = rng.integers(0, 8, nt).astype(np.int32)
+    lens = rng.integers(0, 90, nq)
+    lens[:5] = 0
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    cand = np.concatenate([rng.permutation(nt)[:n] for n in lens] + [np.empty(0, np.int64)]).astype(np.int32)
+    for i in range(5, 40):  # make sure the true source and the duplicates are among the candidates of some queries
+        if lens[i] >= 3:
+            cand[off[i]:off[i] + 3] = (17, 5, 9)
+            query[i] = train[9]
+    want = O.hamming_best2(query, train, off, cand, level)
+    got = hamming_best2(query, train, off, cand, level)
+    assert np.array_equal(got, want)
+    assert np.array_equal(hamming_best2(query, train, off, cand, None)[:, [0, 1, 3]], want[:, [0, 1, 3]])
+    assert (got[:5] == np.array([-1, 256, -1, 256, -1])).all()

@@ -146,3 +146,23 @@ def test_select_semantic_keys_is_the_reference_loop():
         if classes[row, col] <= 8:
             want_keep.append(i)
     assert keep.tolist() == want_keep
+
+
+def test_hamming_best2_tie_and_demotion_rules():
+    """The SearchByProjection candidate loop (ORBmatcher.cc:79-113): strict '<' keeps the first minimum; a later equal distance
+    becomes the second best; a beaten best is demoted together with its level."""
+    def desc(nbits):
+        d = np.zeros(32, np.uint8)
+        for b in range(nbits):
+            d[b >> 3] |= 1 << (b & 7)
+        return d
+    q = np.zeros((1, 32), np.uint8)
+    train = np.stack([desc(5), desc(3), desc(3), desc(7)])
+    level = np.array([10, 11, 12, 13])
+    r = O.hamming_best2(q, train, [0, 4], [0, 1, 2, 3], level)[0]
+    assert r.tolist() == [1, 3, 11, 3, 12]  # idx 2 ties with the best and becomes second best
+    r = O.hamming_best2(q, train, [0, 2], [0, 1], level)[0]
+    assert r.tolist() == [1, 3, 11, 5, 10]  # idx 0 was best, then demoted with its level
+    r = O.hamming_best2(q, train, [0, 2], [1, 0], level)[0]
+    assert r.tolist() == [1, 3, 11, 5, 10]
+    assert O.hamming_best2(q, train, [0, 0], [], level)[0].tolist() == [-1, 256, -1, 256, -1]
