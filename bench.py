@@ -154,27 +154,51 @@ def load_weights(net, model):
     return read_caffemodel(model)
 
 
+def conv_flops(net):
+    """(shared, per_sample) algorithmic convolution flops of a net: 2 Cin k^2 Cout H W per layer, split at the first sampling
+    Dropout (everything upstream is sample-invariant; SURVEY 8d: Basic 52.00 + T 195.11 GF, Standard 134.12 + T 311.84 GF)."""
+    from sivo_b200.prototxt import blob_shapes
+    shapes = blob_shapes(net)
+    shared = per = 0.0
+    sampled = False
+    for ly in net.layers:
+        if ly.type == "Dropout" and ly.sample_weights_test:
+            sampled = True
+        if ly.type == "Convolution":
+            cin = shapes[ly.bottoms[0]][0]
+            cout, ho, wo = shapes[ly.tops[0]]
+            f = 2.0 * cin * ly.kernel * ly.kernel * cout * ho * wo
+            if sampled:
+                per += f
+            else:
+                shared += f
+    return shared, per
+
+
 def run_reference(args, rank, world):
     """Reference arm: the CPU restatement of the reference path (the reference itself cannot be built here) on all
-    host cores.  A full frame costs ~14 s, so one step is a bounded sample of the frame -- SegNet(T) on the centre band of
-    `BAND` rows of the network input (the net is fully convolutional: cost is linear in pixels) plus the two full extractor
-    calls -- and the frame time is band_time * (H / BAND) + orb_time.  Exactly --steps timed steps after --warmup untimed ones."""
+    host cores.  A full frame costs ~14 s, so one step is a bounded sample of the frame: the same network at full resolution with
+    T_S = 2 Monte-Carlo samples instead of T (same layers, same shapes, fewer repetitions of the per-sample part), scaled by the
+    flop ratio (shared + T per_sample) / (shared + T_S per_sample), plus the two full extractor calls.
+    Exactly --steps timed steps after --warmup untimed ones."""
     if rank != 0:
         return
     import gen_prototxt
     from sivo_b200.prototxt import load_net
-    BAND = 96  # rows; a multiple of 32 so that both models pool it cleanly
+    T_S = 2
     T = args.T or (6 if args.model == "basic" else 12)
     net, proto, model, weights = model_files(args.model, T, os.path.join("/tmp", "sivo_b200_models"))
     weights = weights or load_weights(net, model)
-    band_net = load_net(getattr(gen_prototxt, args.model)(T=T, H=BAND, W=NET_W))
+    sample_net = load_net(getattr(gen_prototxt, args.model)(T=T_S))
+    shared, per = conv_flops(net)
+    scale = (shared + T * per) / (shared + T_S * per)
     cores = os.cpu_count() or 1
     fr = frames(1)
     times = []
     for i in range(args.warmup + args.steps):
-        a, b = cpu_reference_frame(band_net, weights, fr[0][0], fr[0][1], fr[0][2], args.nfeatures, cores)
+        a, b = cpu_reference_frame(sample_net, weights, fr[0][0], fr[0][1], fr[0][2], args.nfeatures, cores)
         if i >= args.warmup:
-            times.append(a * (NET_H / BAND) + b)
+            times.append(a * scale + b)
     ms = 1e3 * float(np.mean(times))
     fps = 1e3 / ms
     line = {"impl": "reference", "metric": "frames/sec SegNet(T)+ORB", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
@@ -182,8 +206,10 @@ def run_reference(args, rank, world):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, T),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": f"per step: SegNet {args.model} T={T} (torch-CPU fp32 restatement) on the centre {BAND} of {NET_H} rows, "
-                                       f"scaled by {NET_H}/{BAND}, + ORB({args.nfeatures}) x2 on the full images (cv2 composition, two threads)"},
+                             "sample": f"per step: SegNet {args.model} at full resolution with T={T_S} of {T} samples (torch-CPU fp32 restatement), "
+                                       f"time scaled by the flop ratio {scale:.3f} = ({shared / 1e9:.1f} + {T} x {per / 1e9:.1f}) / "
+                                       f"({shared / 1e9:.1f} + {T_S} x {per / 1e9:.1f}) GF, + ORB({args.nfeatures}) x2 on the full images "
+                                       f"(cv2 composition, two threads)"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 

@@ -381,7 +381,7 @@ SegNet::SegNet(const std::string& prototxt, const std::string& caffemodel, const
 
 SegNet::~SegNet() {
   cudaSetDevice(device_);
-  if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+  for (auto& g : graphs_) cudaGraphExecDestroy(g.exec);
   for (auto e : events_) cudaEventDestroy(e);
   if (stream_) cudaStreamDestroy(stream_);
 }
@@ -527,8 +527,14 @@ void SegNet::run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* co
   static const bool graphs_enabled = [] { const char* e = std::getenv("SIVO_B200_NO_GRAPH"); return !(e && e[0] == '1'); }();
   if (graphs_enabled && graph_ok_ && all_tc) {
     const void* key[5] = {bgr_dev, classes_dev, conf_dev, ent_dev, s};
-    if (!graph_exec_ || memcmp(key, graph_key_, sizeof key) != 0) {
-      if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+    cudaGraphExec_t graph_exec_ = nullptr;
+    for (size_t i = 0; i < graphs_.size(); ++i)
+      if (memcmp(key, graphs_[i].key, sizeof key) == 0) {
+        std::rotate(graphs_.begin(), graphs_.begin() + i, graphs_.begin() + i + 1);  // move to front
+        graph_exec_ = graphs_.front().exec;
+        break;
+      }
+    if (!graph_exec_) {
       cudaGraph_t g = nullptr;
       cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
       if (e == cudaSuccess) {
@@ -549,7 +555,14 @@ void SegNet::run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* co
         graph_ok_ = false;
         graph_exec_ = nullptr;
       } else {
-        memcpy(graph_key_, key, sizeof key);
+        if (graphs_.size() >= kMaxGraphs) {  // a caller cycling through more buffers than this re-captures the oldest
+          cudaGraphExecDestroy(graphs_.back().exec);
+          graphs_.pop_back();
+        }
+        GraphEntry ge;
+        memcpy(ge.key, key, sizeof key);
+        ge.exec = graph_exec_;
+        graphs_.insert(graphs_.begin(), ge);
       }
     }
     if (graph_exec_) {

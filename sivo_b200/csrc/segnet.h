@@ -97,8 +97,10 @@ class SegNet {
   PinnedBuf h_kp_, h_kp_out_;
   std::vector<cudaEvent_t> events_;
   // the op list captured once as a CUDA graph (one launch per frame); re-captured if the buffers or the stream change
-  cudaGraphExec_t graph_exec_ = nullptr;
-  const void* graph_key_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // captured op lists, one per (input, outputs, stream) pointer set the caller has used; most recently used first
+  struct GraphEntry { const void* key[5]; cudaGraphExec_t exec; };
+  std::vector<GraphEntry> graphs_;
+  static constexpr size_t kMaxGraphs = 16;
   bool graph_ok_ = true;
 };
 
