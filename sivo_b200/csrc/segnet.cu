@@ -382,6 +382,8 @@ SegNet::SegNet(const std::string& prototxt, const std::string& caffemodel, const
 SegNet::~SegNet() {
   cudaSetDevice(device_);
   for (auto& g : graphs_) cudaGraphExecDestroy(g.exec);
+  for (auto e : band_ev_) cudaEventDestroy(e);
+  if (copy_stream_) cudaStreamDestroy(copy_stream_);
   for (auto e : events_) cudaEventDestroy(e);
   if (stream_) cudaStreamDestroy(stream_);
 }
@@ -446,6 +448,7 @@ void SegNet::enqueue(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_
         break;
       }
       case Op::Reduce: {
+        if (skip_reduce_) break;
         const TensorView& lv = tensors_[op.in]->v;
         launch_mc_reduce(static_cast<const float*>(lv.p), lv.n, lv.c, lv.cs, lv.h * lv.w, classes_dev, conf_dev, ent_dev, s);
         break;
@@ -526,7 +529,8 @@ void SegNet::run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* co
   for (const Op& op : ops_) if (op.kind == Op::Conv && !op.use_tc) all_tc = false;  // the SIMT launcher sets attributes per launch
   static const bool graphs_enabled = [] { const char* e = std::getenv("SIVO_B200_NO_GRAPH"); return !(e && e[0] == '1'); }();
   if (graphs_enabled && graph_ok_ && all_tc) {
-    const void* key[5] = {bgr_dev, classes_dev, conf_dev, ent_dev, s};
+    const void* key[5] = {bgr_dev, classes_dev, conf_dev, ent_dev,
+                          reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(s) ^ (skip_reduce_ ? 1u : 0u))};
     cudaGraphExec_t graph_exec_ = nullptr;
     for (size_t i = 0; i < graphs_.size(); ++i)
       if (memcmp(key, graphs_[i].key, sizeof key) == 0) {
@@ -596,14 +600,52 @@ void SegNet::run_host(const uint8_t* bgr, int rows, int cols, size_t stride, uin
       memcpy(stage + static_cast<size_t>(y) * W_ * 3, src + static_cast<size_t>(y) * stride, static_cast<size_t>(W_) * 3);
     SIVO_CUDA(cudaMemcpyAsync(d_bgr_.p, stage, hw * 3, cudaMemcpyHostToDevice, stream_));
   }
-  run_device(d_bgr_.as<uint8_t>(), d_classes_.as<uint8_t>(), d_conf_.as<double>(), d_ent_.as<double>(), stream_);
   // outputs are caller-owned plain memory (Frame copies them into itself, Frame.cc:239-241): page-locked caller
   // buffers receive the device copy directly, pageable ones go through the pinned staging buffers
   const bool pc = is_pinned_host(classes), pf = is_pinned_host(conf), pe = is_pinned_host(ent);
-  if (classes) SIVO_CUDA(cudaMemcpyAsync(pc ? static_cast<void*>(classes) : h_classes_.p, d_classes_.p, hw, cudaMemcpyDeviceToHost, stream_));
-  if (conf) SIVO_CUDA(cudaMemcpyAsync(pf ? static_cast<void*>(conf) : h_conf_.p, d_conf_.p, hw * sizeof(double), cudaMemcpyDeviceToHost, stream_));
-  if (ent) SIVO_CUDA(cudaMemcpyAsync(pe ? static_cast<void*>(ent) : h_ent_.p, d_ent_.p, hw * sizeof(double), cudaMemcpyDeviceToHost, stream_));
-  SIVO_CUDA(cudaStreamSynchronize(stream_));
+  uint8_t* hc = pc ? classes : h_classes_.as<uint8_t>();
+  double* hf = pf ? conf : h_conf_.as<double>();
+  double* he = pe ? ent : h_ent_.as<double>();
+  static const int n_bands = [] { const char* e = std::getenv("SIVO_B200_READBACK_BANDS"); return e ? std::max(1, std::min(16, atoi(e))) : 1; }();  // opt-in: measured no gain with the extractors' copies sharing the D2H engine
+  const Op& last = ops_.back();
+  const TensorView* lv = last.kind == Op::Reduce ? &tensors_[last.in]->v : nullptr;
+  const bool banded = n_bands > 1 && !profiling_ && lv && lv->cs == 16 && lv->c <= 16 && (classes || conf || ent) && H_ >= n_bands;
+  if (!banded) {
+    run_device(d_bgr_.as<uint8_t>(), d_classes_.as<uint8_t>(), d_conf_.as<double>(), d_ent_.as<double>(), stream_);
+    if (classes) SIVO_CUDA(cudaMemcpyAsync(hc, d_classes_.p, hw, cudaMemcpyDeviceToHost, stream_));
+    if (conf) SIVO_CUDA(cudaMemcpyAsync(hf, d_conf_.p, hw * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    if (ent) SIVO_CUDA(cudaMemcpyAsync(he, d_ent_.p, hw * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    SIVO_CUDA(cudaStreamSynchronize(stream_));
+  } else {
+    if (!copy_stream_) SIVO_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    while (static_cast<int>(band_ev_.size()) < n_bands) {
+      cudaEvent_t e;
+      SIVO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      band_ev_.push_back(e);
+    }
+    skip_reduce_ = true;
+    try {
+      run_device(d_bgr_.as<uint8_t>(), d_classes_.as<uint8_t>(), d_conf_.as<double>(), d_ent_.as<double>(), stream_);
+    } catch (...) {
+      skip_reduce_ = false;
+      throw;
+    }
+    skip_reduce_ = false;
+    for (int b = 0; b < n_bands; ++b) {
+      const int r0 = static_cast<int>(static_cast<long>(H_) * b / n_bands), r1 = static_cast<int>(static_cast<long>(H_) * (b + 1) / n_bands);
+      const size_t p0 = static_cast<size_t>(r0) * W_, np = static_cast<size_t>(r1 - r0) * W_;
+      launch_mc_reduce(static_cast<const float*>(lv->p), lv->n, lv->c, lv->cs, lv->h * lv->w, d_classes_.as<uint8_t>(), d_conf_.as<double>(),
+                       d_ent_.as<double>(), stream_, static_cast<int>(p0), static_cast<int>(np));
+      SIVO_CUDA(cudaEventRecord(band_ev_[b], stream_));
+      SIVO_CUDA(cudaStreamWaitEvent(copy_stream_, band_ev_[b], 0));
+      if (classes) SIVO_CUDA(cudaMemcpyAsync(hc + p0, d_classes_.as<uint8_t>() + p0, np, cudaMemcpyDeviceToHost, copy_stream_));
+      if (conf) SIVO_CUDA(cudaMemcpyAsync(hf + p0, d_conf_.as<double>() + p0, np * sizeof(double), cudaMemcpyDeviceToHost, copy_stream_));
+      if (ent) SIVO_CUDA(cudaMemcpyAsync(he + p0, d_ent_.as<double>() + p0, np * sizeof(double), cudaMemcpyDeviceToHost, copy_stream_));
+    }
+    launches = static_cast<int>(ops_.size()) - 1 + n_bands;  // the bands replace the single Reduce launch of the op list
+    SIVO_CUDA(cudaStreamSynchronize(copy_stream_));
+    SIVO_CUDA(cudaStreamSynchronize(stream_));
+  }
   if (classes && !pc) memcpy(classes, h_classes_.p, hw);
   if (conf && !pf) memcpy(conf, h_conf_.p, hw * sizeof(double));
   if (ent && !pe) memcpy(ent, h_ent_.p, hw * sizeof(double));

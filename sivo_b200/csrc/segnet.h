@@ -102,6 +102,11 @@ class SegNet {
   std::vector<GraphEntry> graphs_;
   static constexpr size_t kMaxGraphs = 16;
   bool graph_ok_ = true;
+  // segmentImage read-back overlap: the MC reduction runs in row bands and each band's slices of the three maps start their
+  // device-to-host copy on a second stream while the next band is reduced
+  bool skip_reduce_ = false;      // set by run_host around run_device: the op list stops before the Reduce op
+  cudaStream_t copy_stream_ = nullptr;
+  std::vector<cudaEvent_t> band_ev_;
 };
 
 // conv_tc.cu -- tcgen05 implicit-GEMM convolution

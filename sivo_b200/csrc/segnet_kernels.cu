@@ -325,14 +325,14 @@ __global__ void k_mc_reduce(const float* __restrict__ logits, int T, int cs, int
 // sample and there are 4x more threads in flight, which is what this HBM-bound pass needs.  The softmax max / sum and
 // the final argmax / entropy are combined with xor-shuffles inside the 4-lane group (first maximum still wins).
 __global__ void k_mc_reduce_quad(const float* __restrict__ logits, int T, int C, int hw, uint8_t* __restrict__ classes,
-                                 double* __restrict__ conf, double* __restrict__ entropy) {
+                                 double* __restrict__ conf, double* __restrict__ entropy, int pix0, int pix_end) {
   // Instruction diet (ncu: the first version was issue-bound at 3400 instructions per warp, 0.8 TB/s): one IEEE
   // reciprocal per sample instead of C divisions (p = e * (1/sum), <= 1 ulp from e/sum), mean = acc * (1/T) in double,
   // and log2 evaluated in float on the double mean (relative error < 2^-22, i.e. < 1e-6 on the entropy, against the
   // 1e-4 the contract allows); the products and the sums stay in double like computeEntropy (bayesian_segnet.cpp:38-44).
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int pix = gid >> 2, q = gid & 3;
-  const bool live = pix < hw;
+  const int pix = pix0 + (gid >> 2), q = gid & 3;
+  const bool live = pix < pix_end;
   const int pp = live ? pix : hw - 1;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   constexpr int kBatch = 6;  // samples whose loads are issued together (memory-level parallelism: the pass is HBM-bound)
@@ -686,9 +686,17 @@ void launch_dropout_unpool(TensorView in, int T, const uint8_t* mask, int mask_n
 }
 
 void launch_mc_reduce(const float* logits, int T, int C, int cs, int hw, uint8_t* classes, double* conf, double* entropy,
-                      cudaStream_t s) {
-  if (cs == 16 && C <= 16) k_mc_reduce_quad<<<blocks_for(static_cast<size_t>(hw) * 4, 256), 256, 0, s>>>(logits, T, C, hw, classes, conf, entropy);
-  else if (C == 15) k_mc_reduce<15><<<blocks_for(hw, 128), 128, 0, s>>>(logits, T, cs, hw, classes, conf, entropy);
+                      cudaStream_t s, int pix0, int npix) {
+  if (npix < 0) { pix0 = 0; npix = hw; }
+  if (pix0 < 0 || pix0 + npix > hw) fail(SIVO_EINVAL, "mc_reduce: pixel range outside the map");
+  if (npix == 0) return;
+  if (cs == 16 && C <= 16) {
+    k_mc_reduce_quad<<<blocks_for(static_cast<size_t>(npix) * 4, 256), 256, 0, s>>>(logits, T, C, hw, classes, conf, entropy, pix0, pix0 + npix);
+    SIVO_CUDA(cudaGetLastError());
+    return;
+  }
+  if (pix0 != 0 || npix != hw) fail(SIVO_EINVAL, "mc_reduce: pixel ranges need the 16-channel logits layout");
+  if (C == 15) k_mc_reduce<15><<<blocks_for(hw, 128), 128, 0, s>>>(logits, T, cs, hw, classes, conf, entropy);
   else k_mc_reduce_generic<<<blocks_for(hw, 128), 128, 0, s>>>(logits, T, C, cs, hw, classes, conf, entropy);
   SIVO_CUDA(cudaGetLastError());
 }

@@ -56,8 +56,9 @@ void launch_unpool(TensorView in, const uint8_t* mask, int mask_n, TensorView ou
 // in.n may be 1 (broadcast to out.n samples)
 void launch_dropout(TensorView in, TensorView out, const DropoutParams& d, float scale, cudaStream_t s);
 // logits: float [T, H, W, 16]
+// pix0 / npix restrict the pass to pixels [pix0, pix0 + npix) (npix < 0: all of them)
 void launch_mc_reduce(const float* logits, int T, int C, int cs, int hw, uint8_t* classes, double* conf,
-                      double* entropy, cudaStream_t s);
+                      double* entropy, cudaStream_t s, int pix0 = 0, int npix = -1);
 void launch_dropout_bits(uint64_t seed, const uint64_t* frame_dev, int layer, int T, int C, int H, int W,
                          uint8_t* keep_nchw, cudaStream_t s);
 // layout converters for the test hooks (float NCHW host order <-> NHWC activation)
