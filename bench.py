@@ -270,11 +270,17 @@ def main():
     rec_bytes = record.record_bytes(hw, kp_cap)
     offs = record.offsets(hw, kp_cap)
     o_cls, o_conf, o_ent, o_kp = offs["classes"], offs["confidence"], offs["entropy"], offs["kp_left"]
-    d_rec = torch.zeros(rec_bytes, dtype=torch.uint8, device=dev)
-    d_all = torch.empty(rec_bytes * world, dtype=torch.uint8, device=dev) if world > 1 else None
-    h_rec_t = torch.zeros(rec_bytes, dtype=torch.uint8).pin_memory()
-    h_rec = h_rec_t.numpy()
+    # double-buffered: the gather of frame i runs on a side stream under the convolutions of frame i+1.  SegNet writes its
+    # three maps straight into the record (no device-to-device packing copies).
+    d_rec = [torch.zeros(rec_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    d_all = [torch.empty(rec_bytes * world, dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
+    h_rec_t = [torch.zeros(rec_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    h_rec = [t.numpy() for t in h_rec_t]
     stream = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev) if world > 1 else None
+    ev_main = [torch.cuda.Event() for _ in range(2)]
+    ev_side = [torch.cuda.Event() for _ in range(2)]
+    side_used = [False, False]
 
     prof = {"segnet_launch": 0.0, "orb": 0.0, "pack": 0.0, "gather": 0.0}
 
@@ -286,7 +292,14 @@ def main():
     def device_step(i):
         j = i % n_frames
         t0 = time.perf_counter()
-        seg.run_device(d_bgr[j].data_ptr(), d_cls.data_ptr(), d_conf.data_ptr(), d_ent.data_ptr(), stream.cuda_stream)
+        k = i & 1
+        if world > 1:
+            if side_used[k]:
+                stream.wait_event(ev_side[k])  # the gather that last read this record has finished
+            base = d_rec[k].data_ptr()
+            seg.run_device(d_bgr[j].data_ptr(), base + o_cls, base + o_conf, base + o_ent, stream.cuda_stream)
+        else:
+            seg.run_device(d_bgr[j].data_ptr(), d_cls.data_ptr(), d_conf.data_ptr(), d_ent.data_ptr(), stream.cuda_stream)
         t1 = time.perf_counter()
         fr_ = pool.submit(orb_r.run_device_input, d_gr[j].data_ptr(), NET_H, NET_W, NET_W)
         out = [orb_l.run_device_input(d_gl[j].data_ptr(), NET_H, NET_W, NET_W), None]
@@ -294,14 +307,18 @@ def main():
         t2 = time.perf_counter()
         t3 = t2
         if world > 1:
-            record.pack_host_part(h_rec, hw, kp_cap, rank * 100000 + i, out[0][0], out[0][1], out[1][0], out[1][1])
+            if side_used[k]:
+                ev_main[k].synchronize()  # the upload that last read this pinned buffer (two frames ago) has been consumed
+            record.pack_host_part(h_rec[k], hw, kp_cap, rank * 100000 + i, out[0][0], out[0][1], out[1][0], out[1][1])
             t3 = time.perf_counter()
-            d_rec[:record.HEADER].copy_(h_rec_t[:record.HEADER], non_blocking=True)
-            d_rec[o_cls:o_cls + hw].copy_(d_cls, non_blocking=True)
-            d_rec[o_conf:o_conf + hw * 8].copy_(d_conf.view(torch.uint8), non_blocking=True)
-            d_rec[o_ent:o_ent + hw * 8].copy_(d_ent.view(torch.uint8), non_blocking=True)
-            d_rec[o_kp:].copy_(h_rec_t[o_kp:], non_blocking=True)
-            dist.all_gather_into_tensor(d_all, d_rec)
+            d_rec[k][:record.HEADER].copy_(h_rec_t[k][:record.HEADER], non_blocking=True)
+            d_rec[k][o_kp:].copy_(h_rec_t[k][o_kp:], non_blocking=True)
+            ev_main[k].record(stream)
+            with torch.cuda.stream(side):
+                side.wait_event(ev_main[k])
+                dist.all_gather_into_tensor(d_all[k], d_rec[k])
+                ev_side[k].record(side)
+            side_used[k] = True
         t4 = time.perf_counter()
         prof["segnet_launch"] += t1 - t0
         prof["orb"] += t2 - t1

@@ -100,7 +100,7 @@ class SegNet {
   // captured op lists, one per (input, outputs, stream) pointer set the caller has used; most recently used first
   struct GraphEntry { const void* key[5]; cudaGraphExec_t exec; };
   std::vector<GraphEntry> graphs_;
-  static constexpr size_t kMaxGraphs = 16;
+  static constexpr size_t kMaxGraphs = 32;
   bool graph_ok_ = true;
   // segmentImage read-back overlap: the MC reduction runs in row bands and each band's slices of the three maps start their
   // device-to-host copy on a second stream while the next band is reduced
