@@ -240,6 +240,12 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # The gather overlaps the next frame's convolutions, whose grids are sized to the 148 SMs (conv_decode1: 288 CTAs = two
+        # waves of 144).  A default NCCL all-gather takes a dozen SMs and would push them into a third wave, so keep it to a
+        # few channels: 6.4 MB per rank needs little bandwidth (measured at N=2: 8 channels 1278 fps, 2: 1425, 1: 1443).
+        nch = "1" if world <= 2 else ("2" if world <= 4 else "4")  # <= 4 SMs: conv_decode1 keeps its two waves
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", nch)
+        os.environ.setdefault("NCCL_MAX_CTAS", nch)
         dist.init_process_group("nccl", device_id=dev)
     T = args.T or (6 if args.model == "basic" else (12 if world == 1 else 6))
     cache = os.path.join("/tmp", "sivo_b200_models")
