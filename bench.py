@@ -243,7 +243,7 @@ def main():
         # The gather overlaps the next frame's convolutions, whose grids are sized to the 148 SMs (conv_decode1: 288 CTAs = two
         # waves of 144).  A default NCCL all-gather takes a dozen SMs and would push them into a third wave, so keep it to a
         # few channels: 6.4 MB per rank needs little bandwidth (measured at N=2: 8 channels 1278 fps, 2: 1425, 1: 1443).
-        nch = "1" if world <= 2 else ("2" if world <= 4 else "4")  # <= 4 SMs: conv_decode1 keeps its two waves
+        nch = "1" if world <= 2 else "2"  # measured: N=4 2 channels 2899 fps (default 2499); N=8 2 channels 5355, 4: 5175 (default 5013)
         os.environ.setdefault("NCCL_MAX_NCHANNELS", nch)
         os.environ.setdefault("NCCL_MAX_CTAS", nch)
         dist.init_process_group("nccl", device_id=dev)
