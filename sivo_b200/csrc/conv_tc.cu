@@ -1,9 +1,9 @@
 // tcgen05 implicit-GEMM convolution for sm_100a -- replaces cuDNN's fp32 `cudnnConvolutionForward`
-// (caffe/src/caffe/layers/cudnn_conv_layer.cu:21-37) for the SegNet convolutions with 64 input channels
-// (all of Basic except conv1 / the classifier; the 64-channel layers of Standard).
+// (caffe/src/caffe/layers/cudnn_conv_layer.cu:21-37) and the layers fused around it for every SegNet convolution
+// (Basic: all eight 7x7 layers + the 1x1 classifier; Standard: all 26 3x3 layers).
 //
 // GEMM view per CTA:  D[128 pixels x N couts] += A[128 pixels x 64 cin] * B[64 cin x N couts]  per filter tap,
-// M = 128 consecutive pixels of one output row, two output rows (R = 2) per accumulator stage.
+// M = 128 consecutive pixels of one output row, R = 4 (or 2) output rows -- a "row block" -- per accumulator stage.
 //
 //  * Activations are NHWC half, so one pixel's 64 input channels are one 128-byte row: exactly a
 //    SWIZZLE_128B K-major UMMA operand row.  A TMA box {64 ch, 128+K-1 px, 1 row} of the input lands one
@@ -11,12 +11,18 @@
 //  * The A operand of tap (kh, kw) for output row r is the same halo row shifted by kw pixels: the UMMA
 //    shared-memory descriptor simply starts kw*128 bytes later (the swizzle phase follows the absolute address), so
 //    each input row is fetched from L2 once per K rows of output instead of K*K times.
-//  * A CTA walks down a 128-px-wide column strip two output rows at a time with a ring of halo rows:
-//    every input row is loaded once per CTA (plus the K-1 overlap between vertically adjacent CTAs).
-//  * Weights [tap][cout][cin] stream through a 4-stage TMA ring, one {64 cin x N cout} tile per tap.
-//  * Accumulators live in TMEM (2 stages x R x N fp32 columns) so the epilogue of row pair j overlaps the
-//    MMAs of pair j+1.  Warp roles: 0 = halo-row TMA producer, 1 = weight TMA producer, 2 = MMA issuer
-//    (+ TMEM alloc), 3 = second MMA issuer, 4..7 = epilogue (tcgen05.ld -> bias / BN affine / ReLU / dropout -> half -> global).
+//  * A CTA walks down a 128-px-wide column strip one row block at a time with a ring of halo rows: every input row is
+//    loaded once per CTA (plus the K-1 overlap between vertically adjacent CTAs) and released as soon as its last tap
+//    row has been issued.
+//  * Weights stream through a TMA ring, one tile per tap (k_conv_tc: {64 cin x N cout}, [tap][cout][cin]) or per pair of
+//    vertically adjacent taps (k_conv_tc_pair: two stacked tiles, N = 128, [kw][kh][cout][cin]).
+//  * The 3-channel first layer reads a window-folded view of the zero-padded 8-channel image (KW = 1, see conv_tc_plan).
+//  * Accumulators live in TMEM (2 stages x R x N fp32 columns) so the epilogue of block j overlaps the MMAs of block
+//    j+1.  384 threads: warp 0 = halo-row TMA producer, warp 1 = weight TMA producer, warps 2-3 = MMA issuers (+ TMEM
+//    alloc), warps 4-11 = epilogue (two per TMEM lane quarter; setmaxnreg 56 / 216): tcgen05.ld -> bias / BN affine / ReLU
+//    -> half, then store | dropout | max-unpool scatter | 2x2 max-pool + argmax | 1x1 classifier -> float logits.
+//  * Constants (bias, BN, classifier weights) are kernel parameters; stores are 4-lane transposed (quad_transpose): the
+//    MMAs keep the shared-memory / L1 data path busy, so the epilogue must stay off it.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
