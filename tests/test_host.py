@@ -163,3 +163,31 @@ def test_bn_absorber_follows_the_reference_script(tmp_path):
     back = read_caffemodel(str(tmp_path / "merged" / "bn_conv_merged_weights.caffemodel"))
     assert all(np.array_equal(back[k][0], new_w[k][0]) for k in new_w)
     assert open(tmp_path / "merged" / "bn_conv_merged_model.prototxt").read() == new_text
+
+
+def test_caffemodel_reader_survives_damaged_files(model_dir, tmp_path):
+    """8(f)-3 loader hardening: truncated, bit-flipped and random .caffemodel bytes come back as an error code through the C-ABI
+    (never a crash, never a silent success with the wrong shapes).  Without a GPU a file that still parses ends at the first
+    CUDA call (ECUDA); with one, at the layer / shape check (EFORMAT)."""
+    _, _, proto, model = make_model(model_dir, "basic", T=2, H=32, W=64, width=8)
+    raw = open(model, "rb").read()
+    rng = np.random.default_rng(0)
+    cases = [raw[:cut] for cut in (1, 7, len(raw) // 3, len(raw) // 2, len(raw) - 1)]
+    for _ in range(24):
+        b = bytearray(raw)
+        for _ in range(8):
+            b[int(rng.integers(0, min(len(b), 4000)))] = int(rng.integers(0, 256))
+        cases.append(bytes(b))
+    cases.append(bytes(rng.integers(0, 256, 5000, dtype=np.uint8)))
+    p = tmp_path / "damaged.caffemodel"
+    import torch
+    for data in cases:
+        p.write_bytes(data)
+        try:
+            BayesianSegNet(BayesianSegNetParams(proto, str(p)))
+            survived = True
+        except L.SivoError as e:
+            survived = False
+            assert e.code in (L.EFORMAT, L.ECUDA, L.EINVAL), e
+        # a damaged file may only load if the damage left every blob intact in size (a flipped weight byte)
+        assert not survived or (torch.cuda.is_available() and len(data) == len(raw))
