@@ -631,13 +631,18 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // updates acc(r) | acc(r-1) from a single A read.  Per (tap-row pair, kw) that is 5 MMA groups (N = 64, 128, 128,
 // 128, 64) instead of 8: A traffic 80 KB instead of 128 KB per 1024 tensor cycles (141 B/clk), and 20 instead of 32
 // instructions.  Weights come as [kw][kh][cout][cin] so one TMA box of 128 rows lands both taps of a pair.
-template <int K>
+// TRIPLE (K = 7): the last three tap rows (4, 5, 6) are stacked as well -- input row i of that group feeds acc(r) for every
+// r with 0 <= i - r <= 2, one MMA of N = 64 / 128 / 192 / 192 / 128 / 64 per (input row, kw): 1664 tensor cycles instead of
+// 1152 + 768 for a pair plus a single.  The weight stages grow to 24 KB (three 64-row boxes); the halo ring shrinks from
+// K + 3 to 9 slots to pay for it (a block keeps at most 6 rows live, the rest is prefetch depth).
+template <int K, bool TRIPLE = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcParams p,
                const __grid_constant__ TcConsts cst) {
   asm volatile("griddepcontrol.launch_dependents;");
-  constexpr int kRows = 4, RK = kRows + K - 1, kSlots = RK, kPad = (K - 1) / 2, NP = (K + 1) / 2;
-  constexpr int kBBytes = 128 * 128;  // two stacked 64 x 64 weight tiles
+  static_assert(!TRIPLE || K == 7, "the triple group is taps 4..6 of a 7-row filter");
+  constexpr int kRows = 4, RK = kRows + K - 1, kSlots = TRIPLE ? 9 : RK, kPad = (K - 1) / 2, NP = TRIPLE ? 3 : (K + 1) / 2;
+  constexpr int kBBytes = TRIPLE ? 192 * 128 : 128 * 128;  // stacked 64 x 64 weight tiles: stage stride
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_slots = smem;
@@ -703,10 +708,17 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int pp = 0; pp < NP; ++pp)
           for (int kw = 0; kw < K; ++kw) {
             mbar_wait(b_empty + st, ph ^ 1);
-            mbar_expect_tx(b_full + st, static_cast<uint32_t>(kBBytes));
-            // rows (kw*K + 2pp)*64 .. +127 of the [kw][kh][cout] x cin matrix; the odd last tap row drags in 64 rows it
-            // never uses (the next kw's first tap, or zero fill past the end)
-            tma_load_3d(b_stages + st * kBBytes, &map_b, b_full + st, 0, (kw * K + 2 * pp) * 64, w_replica);
+            if (TRIPLE) {  // 64-row boxes: two for a pair, three for the triple group
+              const int nt = pp == 2 ? 3 : 2;
+              mbar_expect_tx(b_full + st, static_cast<uint32_t>(nt * 8192));
+              for (int t = 0; t < nt; ++t)
+                tma_load_3d(b_stages + st * kBBytes + t * 8192, &map_b, b_full + st, 0, (kw * K + 2 * pp + t) * 64, w_replica);
+            } else {
+              mbar_expect_tx(b_full + st, static_cast<uint32_t>(kBBytes));
+              // rows (kw*K + 2pp)*64 .. +127 of the [kw][kh][cout] x cin matrix; the odd last tap row drags in 64 rows it
+              // never uses (the next kw's first tap, or zero fill past the end)
+              tma_load_3d(b_stages + st * kBBytes, &map_b, b_full + st, 0, (kw * K + 2 * pp) * 64, w_replica);
+            }
             if (++st == kBStages) { st = 0; ph ^= 1; }
           }
     }
@@ -714,6 +726,7 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===== MMA issuer (one warp: with N = 128 an MMA lasts 64 tensor cycles and costs 1-2 issue instructions) =====
     const uint32_t idesc64 = (1u << 4) | (static_cast<uint32_t>(64 >> 3) << 17) | (8u << 24);
     const uint32_t idesc128 = (1u << 4) | (static_cast<uint32_t>(128 >> 3) << 17) | (8u << 24);
+    const uint32_t idesc192 = (1u << 4) | (static_cast<uint32_t>(192 >> 3) << 17) | (8u << 24);
     const uint32_t a_base = smem_u32(a_slots), b_base = smem_u32(b_stages);
     int st = 0;
     uint32_t b_phase = 0;
@@ -726,16 +739,17 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t d0 = tmem_base + static_cast<uint32_t>(acc * kRows * 64);  // column of acc(row 3); acc(r) sits at d0 + (3 - r) * 64
       for (int pp = 0; pp < NP; ++pp) {
         const int kh0 = 2 * pp;
+        const bool triple = TRIPLE && pp == 2;
         const bool paired = kh0 + 1 < K;
-        const int last_unit = base_u + kh0 + (paired ? 1 : 0) + kRows - 1;
+        const int last_unit = base_u + kh0 + (triple ? 2 : paired ? 1 : 0) + kRows - 1;
         while (waited <= last_unit && waited < n_units) {
           mbar_wait(a_full + waited % kSlots, (waited / kSlots) & 1);
           ++waited;
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t a_lo[kRows + 1];
+        uint32_t a_lo[kRows + 2];
 #pragma unroll
-        for (int i = 0; i <= kRows; ++i)
+        for (int i = 0; i <= kRows + 1; ++i)
           a_lo[i] = (((a_base + ((base_u + kh0 + i) % kSlots) * kSlotBytes) & 0x3FFFFu) >> 4) | (1u << 16);
 #pragma unroll
         for (int kw = 0; kw < K; ++kw) {
@@ -754,6 +768,20 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                   for (int k = 0; k < 4; ++k)
                     umma_f16(d0 + (3 - r) * 64, hi | (a_lo[r + t] + 2 * k), hi | (b_lo + 512 * t + 2 * k), idesc64,
                              static_cast<uint32_t>(t | k));
+            } else if (triple) {
+              // input row i of the group (block row 4 + i) x taps 4..6: acc(r) for r = i, i-1, i-2 where they exist.
+              // Accumulators sit in decreasing row order, weights in increasing tap order, so each MMA is one contiguous
+              // D range and one contiguous B range: (first acc column, first B row / 64, N)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t ak = 8 * kw + 2 * k;
+                umma_f16(d0 + 3 * 64, hi | (a_lo[0] + ak), hi | (b_lo + 2 * k), idesc64, 1u);          // row 4: acc0 <- W4
+                umma_f16(d0 + 2 * 64, hi | (a_lo[1] + ak), hi | (b_lo + 2 * k), idesc128, 1u);         // row 5: acc1|acc0 <- W4|W5
+                umma_f16(d0 + 1 * 64, hi | (a_lo[2] + ak), hi | (b_lo + 2 * k), idesc192, 1u);         // row 6: acc2|acc1|acc0 <- W4|W5|W6
+                umma_f16(d0, hi | (a_lo[3] + ak), hi | (b_lo + 2 * k), idesc192, 1u);                  // row 7: acc3|acc2|acc1 <- W4|W5|W6
+                umma_f16(d0, hi | (a_lo[4] + ak), hi | (b_lo + 512 + 2 * k), idesc128, 1u);            // row 8: acc3|acc2 <- W5|W6
+                umma_f16(d0, hi | (a_lo[5] + ak), hi | (b_lo + 1024 + 2 * k), idesc64, 1u);            // row 9: acc3 <- W6
+              }
             } else if (paired) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) umma_f16(d0 + 3 * 64, hi | (a_lo[0] + 8 * kw + 2 * k), hi | (b_lo + 2 * k), idesc64, 1u);
@@ -861,6 +889,7 @@ struct ConvTcPlan {
   int kw;             // filter width the kernel walks (== k, or 1 for a window-folded layer)
   bool roll;
   bool pair = false;  // paired-tap kernel (64 -> 64 channels, 4-row blocks)
+  bool triple = false;  // ... with taps 4..6 stacked three-high (K = 7)
   DevBuf w_replicas;  // private replicated copy of the weights (w_rep > 1)
 };
 
@@ -892,7 +921,7 @@ void conv_tc_dispatch(const ConvTcPlan& plan, cudaStream_t s, bool configure) {
     }
   };
   const int K = plan.k;
-  if (plan.pair) { if (K == 7) go(k_conv_tc_pair<7>); else go(k_conv_tc_pair<3>); }
+  if (plan.pair) { if (K == 7 && plan.triple) go(k_conv_tc_pair<7, true>); else if (K == 7) go(k_conv_tc_pair<7>); else go(k_conv_tc_pair<3>); }
   else if (plan.kw == 1 && K > 1) {  // window-folded first layer (K x 1)
     if (!plan.roll) fail(SIVO_EINVAL, "window-folded convolution needs the rolling kernel");
     if (plan.rows == 4) { if (K == 7) go(k_conv_tc<7, true, 4, 1>); else go(k_conv_tc<3, true, 4, 1>); }
@@ -1047,15 +1076,19 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
         SIVO_CUDA(cudaMemcpy(plan->w_replicas.as<uint8_t>() + r * one, op.w_tc_pair.p, one, cudaMemcpyDeviceToDevice));
       wbase = plan->w_replicas.p;
     }
+    const char* triple_env = std::getenv("SIVO_B200_TC_TRIPLE");
+    plan->triple = K == 7 && !(triple_env && triple_env[0] == '0');
     cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(K) * K * 64, static_cast<cuuint64_t>(w_rep)};
     cuuint64_t strides[2] = {128, one};
-    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(plan->triple ? 64 : 128), 1};
     encode(&plan->map_b, wbase, 3, dims, strides, box);
     plan->pair = true;
-    const int slots = rows + K - 1;
-    int st = 6;
-    auto bytes = [&](int n) { return 1024 + static_cast<size_t>(slots) * kSlotBytes + static_cast<size_t>(n) * 16384 + (2 * slots + 2 * n + 4) * 8 + 16 + 64 * 16 * 4; };
+    const int slots = plan->triple ? 9 : rows + K - 1;
+    const size_t stage = plan->triple ? 24576 : 16384;
+    int st = plan->triple ? 3 : 6;
+    auto bytes = [&](int n) { return 1024 + static_cast<size_t>(slots) * kSlotBytes + static_cast<size_t>(n) * stage + (2 * slots + 2 * n + 4) * 8 + 16; };
     while (st > 2 && bytes(st) > 227 * 1024) --st;
+    if (bytes(st) > 227 * 1024) fail(SIVO_EINVAL, "paired-tap kernel does not fit in shared memory");
     p.b_stages = st;
     plan->smem = bytes(st);
   }
