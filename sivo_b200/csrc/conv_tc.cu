@@ -292,7 +292,8 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, const TcConsts& 
       const int c0 = n0 + cc;
       if (p.has_drop && inside && ((c0 & 127) == 0 || cc == 0))
         dropout_bits128(p.seed, *p.frame, p.drop_layer, img, static_cast<uint32_t>(y * p.W + x), c0 >> 7, bits);
-      const uint32_t keep = p.has_drop ? bits[(c0 >> 5) & 3] : 0xFFFFFFFFu;
+      const int wsel = (c0 >> 5) & 3;  // selects, not a dynamically indexed (= local-memory) array
+      const uint32_t keep = !p.has_drop ? 0xFFFFFFFFu : wsel == 0 ? bits[0] : wsel == 1 ? bits[1] : wsel == 2 ? bits[2] : bits[3];
       uint4 e[4];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
@@ -325,21 +326,19 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, const TcConsts& 
               m = __ldg(reinterpret_cast<const uint2*>(p.unpool_mask + (mask_row + xg + j) * p.cout_total + c0 + 8 * cl));
           }
           if (!(row_ok && xg + j < p.W)) continue;
-          const uint32_t mw[2] = {m.x, m.y};                               // 8 mask bytes, channel order
           const uint32_t ew[4] = {e[j].x, e[j].y, e[j].z, e[j].w};         // half2 i = channels 2i, 2i+1 -> mask bytes 2i, 2i+1
+          // the last block's epilogue is exposed at the end of every CTA, so its instruction count matters: one address per
+          // output pixel (the four positions are constant offsets from it) and the eight mask bytes compared four at a time
+          __half* const ob = static_cast<__half*>(p.out) +
+              ((static_cast<size_t>(img) * 2 * p.H + 2 * y) * (2 * p.W) + 2 * (xg + j)) * p.cout_total + c0 + 8 * cl;
+          const size_t row_step = static_cast<size_t>(2 * p.W) * p.cout_total;
 #pragma unroll
           for (int pos = 0; pos < 4; ++pos) {
-            uint32_t sel[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint32_t mb = mw[i >> 1] >> ((i & 1) * 16);
-              const uint32_t lo = ((mb & 0xFFu) == static_cast<uint32_t>(pos)) ? 0x0000FFFFu : 0u;
-              const uint32_t hi2 = (((mb >> 8) & 0xFFu) == static_cast<uint32_t>(pos)) ? 0xFFFF0000u : 0u;
-              sel[i] = ew[i] & (lo | hi2);
-            }
-            *reinterpret_cast<uint4*>(static_cast<__half*>(p.out) +
-                ((static_cast<size_t>(img) * 2 * p.H + 2 * y + (pos >> 1)) * (2 * p.W) + 2 * (xg + j) + (pos & 1)) * p.cout_total + c0 + 8 * cl) =
-                make_uint4(sel[0], sel[1], sel[2], sel[3]);
+            const uint32_t eq0 = __vcmpeq4(m.x, 0x01010101u * pos), eq1 = __vcmpeq4(m.y, 0x01010101u * pos);  // 0xFF per matching byte
+            // bytes (2i, 2i+1) of the mask widen to the two halves of word i
+            const uint32_t s0 = ew[0] & __byte_perm(eq0, 0u, 0x1100), s1 = ew[1] & __byte_perm(eq0, 0u, 0x3322);
+            const uint32_t s2 = ew[2] & __byte_perm(eq1, 0u, 0x1100), s3 = ew[3] & __byte_perm(eq1, 0u, 0x3322);
+            *reinterpret_cast<uint4*>(ob + (pos >> 1) * row_step + (pos & 1) * p.cout_total) = make_uint4(s0, s1, s2, s3);
           }
         }
       } else {
