@@ -386,11 +386,11 @@ __device__ __forceinline__ void epilogue_pool_rows(const TcParams& p, const TcCo
       const uint32_t cand[3] = {b, c, d};
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const __half2 hb = *reinterpret_cast<const __half2*>(&best), hc = *reinterpret_cast<const __half2*>(&cand[k]);
-        const bool lo = __hgt(__low2half(hc), __low2half(hb)), hi = __hgt(__high2half(hc), __high2half(hb));
-        const uint32_t sel = (lo ? 0x0000FFFFu : 0u) | (hi ? 0xFFFF0000u : 0u);
+        // strict '>' per half (false on NaN, like __hgt): 0xFFFF where the candidate wins
+        const uint32_t sel = __hgt2_mask(*reinterpret_cast<const __half2*>(&cand[k]), *reinterpret_cast<const __half2*>(&best));
         best = (best & ~sel) | (cand[k] & sel);
-        arg = (arg & ~((lo ? 0xFFu : 0u) | (hi ? 0xFF00u : 0u))) | ((lo ? static_cast<uint32_t>(k + 1) : 0u) | (hi ? static_cast<uint32_t>(k + 1) << 8 : 0u));
+        const uint32_t selb = __byte_perm(sel, 0u, 0x4420);  // the two half masks as two byte masks (bytes 0 and 1)
+        arg = (arg & ~selb) | ((0x0101u * static_cast<uint32_t>(k + 1)) & selb);
       }
       outv[i >> 1] = best;
       outm[i >> 2] |= arg << (((i >> 1) & 1) * 16);  // two mask bytes per half2, four per 32-bit word
