@@ -246,6 +246,19 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # Run the host side next to the GPU: bind this process (and the threads it starts) to the CPUs NVML names for the device, so
+    # that the pinned buffers and the threads that touch them sit on the GPU's NUMA node.  Undone before the CPU baseline.
+    all_cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h_nv = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)).encode())
+        except Exception:
+            h_nv = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(h_nv)
+    except Exception:
+        pass
     if world > 1:
         # The gather overlaps the next frame's convolutions, whose grids are sized to the 148 SMs (conv_decode1: 288 CTAs = two
         # waves of 144).  A default NCCL all-gather takes a dozen SMs and would push them into a third wave, so keep it to a
@@ -452,6 +465,12 @@ def main():
                 "algorithmic_gflop_per_frame": fl["dedup"] / 1e9, "naive_gflop_per_frame": fl["naive"] / 1e9,
                 "launch_ms": {n: round(float(m), 4) for n, m in zip(names, op_ms)}}
         if not args.no_cpu_baseline and world == 1:
+            if all_cpus:  # the baseline gets every host core again (all threads of the process, incl. any OpenMP workers)
+                try:
+                    for tid in os.listdir("/proc/self/task"):
+                        os.sched_setaffinity(int(tid), all_cpus)
+                except Exception:
+                    os.sched_setaffinity(0, all_cpus)
             w = weights or load_weights(net, model)
             cores = os.cpu_count() or 1
             a, b = cpu_reference_frame(net, w, fr[0][0], fr[0][1], fr[0][2], args.nfeatures, cores)
