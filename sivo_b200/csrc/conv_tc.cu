@@ -634,14 +634,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // r with 0 <= i - r <= 2, one MMA of N = 64 / 128 / 192 / 192 / 128 / 64 per (input row, kw): 1664 tensor cycles instead of
 // 1152 + 768 for a pair plus a single.  The weight stages grow to 24 KB (three 64-row boxes); the halo ring shrinks from
 // K + 3 to 9 slots to pay for it (a block keeps at most 6 rows live, the rest is prefetch depth).
-template <int K, bool TRIPLE = false>
+// NW = accumulator width = output channels per tap tile: 64 for the 64 -> 64 layers; 16 for conv_decode1 composed with the 1x1
+// classifier (float logits straight from the accumulators; needs TRIPLE: its weight boxes are one tap each).
+template <int K, bool TRIPLE = false, int NW = 64>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcParams p,
                const __grid_constant__ TcConsts cst) {
   asm volatile("griddepcontrol.launch_dependents;");
   static_assert(!TRIPLE || K == 7, "the triple group is taps 4..6 of a 7-row filter");
+  static_assert(NW == 64 || (NW == 16 && TRIPLE), "accumulator width");
+  constexpr int kTapBytes = NW * 128;            // one tap's weight tile: NW rows of 64 half
+  constexpr uint32_t kTapLo = kTapBytes >> 4;    // the same in descriptor units
   constexpr int kRows = 4, RK = kRows + K - 1, kSlots = TRIPLE ? 9 : RK, kPad = (K - 1) / 2, NP = TRIPLE ? 3 : (K + 1) / 2;
-  constexpr int kBBytes = TRIPLE ? 192 * 128 : 128 * 128;  // stacked 64 x 64 weight tiles: stage stride
+  constexpr int kBBytes = (TRIPLE ? 3 : 2) * kTapBytes;  // stacked weight tiles: stage stride
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_slots = smem;
@@ -665,7 +670,7 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int npairs = min(p.pairs_per_cta, total_pairs - pair0);
   const int y_base = pair0 * kRows;
   const int n_units = npairs * kRows + K - 1;
-  constexpr uint32_t tmem_cols = 512;  // 2 stages x 4 rows x 64 columns
+  constexpr uint32_t tmem_cols = 2 * kRows * NW;  // 2 stages x 4 rows x NW columns (512 or 128)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kSlots; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
@@ -709,9 +714,9 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_wait(b_empty + st, ph ^ 1);
             if (TRIPLE) {  // 64-row boxes: two for a pair, three for the triple group
               const int nt = pp == 2 ? 3 : 2;
-              mbar_expect_tx(b_full + st, static_cast<uint32_t>(nt * 8192));
+              mbar_expect_tx(b_full + st, static_cast<uint32_t>(nt * kTapBytes));
               for (int t = 0; t < nt; ++t)
-                tma_load_3d(b_stages + st * kBBytes + t * 8192, &map_b, b_full + st, 0, (kw * K + 2 * pp + t) * 64, w_replica);
+                tma_load_3d(b_stages + st * kBBytes + t * kTapBytes, &map_b, b_full + st, 0, (kw * K + 2 * pp + t) * NW, w_replica);
             } else {
               mbar_expect_tx(b_full + st, static_cast<uint32_t>(kBBytes));
               // rows (kw*K + 2pp)*64 .. +127 of the [kw][kh][cout] x cin matrix; the odd last tap row drags in 64 rows it
@@ -723,9 +728,10 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 2) {
     // ===== MMA issuer (one warp: with N = 128 an MMA lasts 64 tensor cycles and costs 1-2 issue instructions) =====
-    const uint32_t idesc64 = (1u << 4) | (static_cast<uint32_t>(64 >> 3) << 17) | (8u << 24);
-    const uint32_t idesc128 = (1u << 4) | (static_cast<uint32_t>(128 >> 3) << 17) | (8u << 24);
-    const uint32_t idesc192 = (1u << 4) | (static_cast<uint32_t>(192 >> 3) << 17) | (8u << 24);
+    // one, two or three tap tiles wide (the names keep the NW = 64 widths)
+    const uint32_t idesc64 = (1u << 4) | (static_cast<uint32_t>(NW >> 3) << 17) | (8u << 24);
+    const uint32_t idesc128 = (1u << 4) | (static_cast<uint32_t>(2 * NW >> 3) << 17) | (8u << 24);
+    const uint32_t idesc192 = (1u << 4) | (static_cast<uint32_t>(3 * NW >> 3) << 17) | (8u << 24);
     const uint32_t a_base = smem_u32(a_slots), b_base = smem_u32(b_stages);
     int st = 0;
     uint32_t b_phase = 0;
@@ -735,7 +741,7 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_wait(t_empty + acc, ((j >> 1) & 1) ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int base_u = j * kRows;
-      const uint32_t d0 = tmem_base + static_cast<uint32_t>(acc * kRows * 64);  // column of acc(row 3); acc(r) sits at d0 + (3 - r) * 64
+      const uint32_t d0 = tmem_base + static_cast<uint32_t>(acc * kRows * NW);  // column of acc(row 3); acc(r) sits at d0 + (3 - r) * NW
       for (int pp = 0; pp < NP; ++pp) {
         const int kh0 = 2 * pp;
         const bool triple = TRIPLE && pp == 2;
@@ -765,7 +771,7 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int r = 0; r < kRows; ++r)
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
-                    umma_f16(d0 + (3 - r) * 64, hi | (a_lo[r + t] + 2 * k), hi | (b_lo + 512 * t + 2 * k), idesc64,
+                    umma_f16(d0 + (3 - r) * NW, hi | (a_lo[r + t] + 2 * k), hi | (b_lo + kTapLo * t + 2 * k), idesc64,
                              static_cast<uint32_t>(t | k));
             } else if (triple) {
               // input row i of the group (block row 4 + i) x taps 4..6: acc(r) for r = i, i-1, i-2 where they exist.
@@ -774,29 +780,29 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint32_t ak = 8 * kw + 2 * k;
-                umma_f16(d0 + 3 * 64, hi | (a_lo[0] + ak), hi | (b_lo + 2 * k), idesc64, 1u);          // row 4: acc0 <- W4
-                umma_f16(d0 + 2 * 64, hi | (a_lo[1] + ak), hi | (b_lo + 2 * k), idesc128, 1u);         // row 5: acc1|acc0 <- W4|W5
-                umma_f16(d0 + 1 * 64, hi | (a_lo[2] + ak), hi | (b_lo + 2 * k), idesc192, 1u);         // row 6: acc2|acc1|acc0 <- W4|W5|W6
+                umma_f16(d0 + 3 * NW, hi | (a_lo[0] + ak), hi | (b_lo + 2 * k), idesc64, 1u);          // row 4: acc0 <- W4
+                umma_f16(d0 + 2 * NW, hi | (a_lo[1] + ak), hi | (b_lo + 2 * k), idesc128, 1u);         // row 5: acc1|acc0 <- W4|W5
+                umma_f16(d0 + 1 * NW, hi | (a_lo[2] + ak), hi | (b_lo + 2 * k), idesc192, 1u);         // row 6: acc2|acc1|acc0 <- W4|W5|W6
                 umma_f16(d0, hi | (a_lo[3] + ak), hi | (b_lo + 2 * k), idesc192, 1u);                  // row 7: acc3|acc2|acc1 <- W4|W5|W6
-                umma_f16(d0, hi | (a_lo[4] + ak), hi | (b_lo + 512 + 2 * k), idesc128, 1u);            // row 8: acc3|acc2 <- W5|W6
-                umma_f16(d0, hi | (a_lo[5] + ak), hi | (b_lo + 1024 + 2 * k), idesc64, 1u);            // row 9: acc3 <- W6
+                umma_f16(d0, hi | (a_lo[4] + ak), hi | (b_lo + kTapLo + 2 * k), idesc128, 1u);         // row 8: acc3|acc2 <- W5|W6
+                umma_f16(d0, hi | (a_lo[5] + ak), hi | (b_lo + 2 * kTapLo + 2 * k), idesc64, 1u);      // row 9: acc3 <- W6
               }
             } else if (paired) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16(d0 + 3 * 64, hi | (a_lo[0] + 8 * kw + 2 * k), hi | (b_lo + 2 * k), idesc64, 1u);
+              for (int k = 0; k < 4; ++k) umma_f16(d0 + 3 * NW, hi | (a_lo[0] + 8 * kw + 2 * k), hi | (b_lo + 2 * k), idesc64, 1u);
 #pragma unroll
               for (int i = 1; i < kRows; ++i)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_f16(d0 + (3 - i) * 64, hi | (a_lo[i] + 8 * kw + 2 * k), hi | (b_lo + 2 * k), idesc128, 1u);
+                  umma_f16(d0 + (3 - i) * NW, hi | (a_lo[i] + 8 * kw + 2 * k), hi | (b_lo + 2 * k), idesc128, 1u);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16(d0, hi | (a_lo[kRows] + 8 * kw + 2 * k), hi | (b_lo + 512 + 2 * k), idesc64, 1u);
+              for (int k = 0; k < 4; ++k) umma_f16(d0, hi | (a_lo[kRows] + 8 * kw + 2 * k), hi | (b_lo + kTapLo + 2 * k), idesc64, 1u);
             } else {
 #pragma unroll
               for (int r = 0; r < kRows; ++r)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_f16(d0 + (3 - r) * 64, hi | (a_lo[r] + 8 * kw + 2 * k), hi | (b_lo + 2 * k), idesc64, 1u);
+                  umma_f16(d0 + (3 - r) * NW, hi | (a_lo[r] + 8 * kw + 2 * k), hi | (b_lo + 2 * k), idesc64, 1u);
             }
             umma_commit(b_empty + st);
           }
@@ -828,14 +834,14 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (p.pool_out) {  // accumulators sit in decreasing row order: row r+1 is 64 columns below row r
         const int r = 2 * eset;
-        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + (3 - r)) * 64);
-        epilogue_pool_rows(p, cst, trow, trow - 64, img, y_base + j * kRows + r, x, 0, lane);
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + (3 - r)) * NW);
+        epilogue_pool_rows(p, cst, trow, trow - NW, img, y_base + j * kRows + r, x, 0, lane);
       } else {
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
           const int r = 2 * eset + rr;
           const int y = y_base + j * kRows + r;
-          const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + (3 - r)) * 64);
+          const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + (3 - r)) * NW);
           epilogue_row(p, cst, trow, img, y, x, 0, lane);
         }
       }
@@ -889,6 +895,7 @@ struct ConvTcPlan {
   bool roll;
   bool pair = false;  // paired-tap kernel (64 -> 64 channels, 4-row blocks)
   bool triple = false;  // ... with taps 4..6 stacked three-high (K = 7)
+  bool nw16 = false;    // ... with 16-wide accumulators: conv composed with the 1x1 classifier (experimental)
   DevBuf w_replicas;  // private replicated copy of the weights (w_rep > 1)
 };
 
@@ -920,7 +927,8 @@ void conv_tc_dispatch(const ConvTcPlan& plan, cudaStream_t s, bool configure) {
     }
   };
   const int K = plan.k;
-  if (plan.pair) { if (K == 7 && plan.triple) go(k_conv_tc_pair<7, true>); else if (K == 7) go(k_conv_tc_pair<7>); else go(k_conv_tc_pair<3>); }
+  if (plan.pair && plan.nw16) go(k_conv_tc_pair<7, true, 16>);
+  else if (plan.pair) { if (K == 7 && plan.triple) go(k_conv_tc_pair<7, true>); else if (K == 7) go(k_conv_tc_pair<7>); else go(k_conv_tc_pair<3>); }
   else if (plan.kw == 1 && K > 1) {  // window-folded first layer (K x 1)
     if (!plan.roll) fail(SIVO_EINVAL, "window-folded convolution needs the rolling kernel");
     if (plan.rows == 4) { if (K == 7) go(k_conv_tc<7, true, 4, 1>); else go(k_conv_tc<3, true, 4, 1>); }
@@ -1145,6 +1153,51 @@ void conv_tc_set_classifier(ConvTcPlan& plan, const float* w_cin_by_cout, int st
   for (int j = 0; j < 16; ++j) plan.cst.cls_b[j] = j < n_bias ? bias[j] : 0.f;
   plan.p.has_cls = 1;
   plan.p.cls_out = logits;
+}
+
+bool conv_tc_can_compose_classifier(const ConvTcPlan& plan) {
+  return plan.pair && plan.triple && plan.k == 7 && !plan.p.out_f32 && !plan.p.unpool_mask && !plan.p.has_drop && !plan.p.pool_out &&
+         !plan.p.has_cls && !plan.p.relu && !plan.p.has_bn && plan.p.cout_total == 64;
+}
+
+void conv_tc_set_composed_classifier(ConvTcPlan& plan, const Op& conv, const float* wc, const float* bc, int n_cls, float* logits) {
+  const int K = 7;
+  if (n_cls > 16 || conv.h_w_raw.size() != static_cast<size_t>(64) * 64 * K * K || conv.h_bias.size() < 64)
+    fail(SIVO_EINVAL, "composed classifier: unexpected layer shapes");
+  // W'[o][i][kh][kw] = sum_c wc[o][c] W[c][i][kh][kw] in double, rounded once to half; rows o >= n_cls stay zero.
+  // Device layout [kw][kh][16][64]: one 16-row TMA box per tap, K-major rows like every other B tile.
+  std::vector<__half> w(static_cast<size_t>(K) * K * 16 * 64, __float2half_rn(0.f));
+  const float* W = conv.h_w_raw.data();
+  for (int o = 0; o < n_cls; ++o)
+    for (int i = 0; i < 64; ++i)
+      for (int kh = 0; kh < K; ++kh)
+        for (int kw = 0; kw < K; ++kw) {
+          double acc = 0.0;
+          for (int c = 0; c < 64; ++c) acc += static_cast<double>(wc[o * 64 + c]) * W[((static_cast<size_t>(c) * 64 + i) * K + kh) * K + kw];
+          w[((static_cast<size_t>(kw) * K + kh) * 16 + o) * 64 + i] = __float2half_rn(static_cast<float>(acc));
+        }
+  plan.w_replicas.alloc(w.size() * sizeof(__half));
+  SIVO_CUDA(cudaMemcpy(plan.w_replicas.p, w.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(K) * K * 16, 1};
+  cuuint64_t strides[2] = {128, static_cast<cuuint64_t>(K) * K * 16 * 128};
+  cuuint32_t box[3] = {64, 16, 1};
+  encode(&plan.map_b, plan.w_replicas.p, 3, dims, strides, box);
+  std::memset(&plan.cst, 0, sizeof(TcConsts));
+  for (int o = 0; o < n_cls; ++o) {
+    double acc = bc[o];
+    for (int c = 0; c < 64; ++c) acc += static_cast<double>(wc[o * 64 + c]) * conv.h_bias[c];
+    plan.cst.bias[o] = static_cast<float>(acc);
+  }
+  TcParams& p = plan.p;
+  p.out_f32 = 1;
+  p.n_tile = 16;
+  p.cout_total = 16;
+  p.out = logits;
+  p.w_rep = 1;
+  p.b_stages = 6;
+  plan.nw16 = true;
+  plan.smem = 1024 + static_cast<size_t>(9) * kSlotBytes + static_cast<size_t>(p.b_stages) * 3 * 16 * 128 + (2 * 9 + 2 * p.b_stages + 4) * 8 + 16;
+  conv_tc_dispatch(plan, nullptr, true);
 }
 
 void conv_tc_launch(const ConvTcPlan& plan, const Op& op, cudaStream_t s) {

@@ -57,6 +57,7 @@ void SegNet::prepare_conv(Op& op, const std::vector<Blob>& cb, const std::vector
         ws[(static_cast<size_t>(tap) * op.cin_p + cidx) * op.cout_p + co] = half ? through_half(v) : v;
       }
   op.h_w = ws;
+  op.h_w_raw.assign(W, W + static_cast<size_t>(cout) * cin * K * K);
   op.w_simt.alloc(ws.size() * sizeof(float));
   SIVO_CUDA(cudaMemcpy(op.w_simt.p, ws.data(), ws.size() * sizeof(float), cudaMemcpyHostToDevice));
   if (half) {  // tensor-core layout: [tap][cout_p][cin_p] half, K(=cin)-major rows
@@ -221,8 +222,13 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
             ops_.back().kind == Op::Conv && ops_.back().use_tc && ops_.back().out == in && conv_tc_can_fuse_classifier(*ops_.back().tc)) {
           // 1x1 classifier straight after a tensor-core convolution: computed in that convolution's epilogue from the
           // half-rounded activations, so the 64-channel tensor is never written or re-read
-          conv_tc_set_classifier(*ops_.back().tc, op.h_w.data(), op.cout_p, op.h_bias.data(), std::min(16, op.cout_p),
-                                 static_cast<float*>(tensors_[op.out]->v.p));
+          const char* compose = std::getenv("SIVO_B200_COMPOSE");
+          if (compose && compose[0] == '1' && !ops_.back().relu && !ops_.back().has_bn && conv_tc_can_compose_classifier(*ops_.back().tc))
+            conv_tc_set_composed_classifier(*ops_.back().tc, ops_.back(), op.h_w_raw.data(), op.h_bias.data(), op.cout,
+                                            static_cast<float*>(tensors_[op.out]->v.p));
+          else
+            conv_tc_set_classifier(*ops_.back().tc, op.h_w.data(), op.cout_p, op.h_bias.data(), std::min(16, op.cout_p),
+                                   static_cast<float*>(tensors_[op.out]->v.p));
           ops_.back().layer += "+" + ly.name;
           ops_.back().flops += op.flops;  // the classifier's multiply-adds run inside that launch
           tensors_[in]->elided = true;

@@ -34,6 +34,7 @@ struct Op {
   float lrn_alpha = 1.f, lrn_beta = 0.75f, lrn_k = 1.f;
   // Conv
   int k = 0, pad = 0, cin = 0, cout = 0, cin_p = 0, cout_p = 0;
+  std::vector<float> h_w_raw;  // the caffemodel's (cout, cin, k, k) floats, unrounded (composed-classifier experiment)
   std::vector<float> h_bias, h_bn_scale, h_bn_shift, h_w;  // host copies (the tensor-core kernels take them as kernel parameters)
   int fold_kw = 0;                  // > 0: KxK conv over 3 channels run as a Kx1 conv over the window-folded padded input (conv_tc.cu)
   int expand_k = 0, expand_blk = 0;  // > 0: a KxK conv over 3 channels run as a 1x1 conv over the tap-expanded input
@@ -125,6 +126,10 @@ void conv_tc_set_pool(ConvTcPlan& plan, void* pooled, uint8_t* mask);
 bool conv_tc_can_fuse_classifier(const ConvTcPlan& plan);
 // host-side weight layout of the paired-tap kernel (64 -> 64 channels)
 std::vector<__half> conv_tc_pair_weights(const float* w_cout_cin_k_k, int K);
+// Experimental (SIVO_B200_COMPOSE=1): conv (64 -> 64, 7x7, no BN / ReLU) followed by the 1x1 classifier run as ONE 64 -> 16
+// convolution with composed weights; logits come straight from the accumulators.  wc = [n_cls][64], bc = [n_cls] (host).
+bool conv_tc_can_compose_classifier(const ConvTcPlan& plan);
+void conv_tc_set_composed_classifier(ConvTcPlan& plan, const Op& conv, const float* wc, const float* bc, int n_cls, float* logits);
 void conv_tc_set_classifier(ConvTcPlan& plan, const float* w_cin_by_cout, int stride, const float* bias, int n_bias, float* logits);  // host pointers
 
 }  // namespace sivo

@@ -272,3 +272,22 @@ def test_bn_absorbed_model_runs_and_agrees(tmp_path):
     (c0, f0, e0), (c1, f1, e1) = outs
     assert (c0 != c1).mean() < 0.02
     assert np.median(np.abs(e0 - e1)) < 5e-3 and np.median(np.abs(f0 - f1)) < 5e-3
+
+
+def test_composed_classifier_experiment_agrees_with_the_two_step_path(model_dir, monkeypatch):
+    """SIVO_B200_COMPOSE=1 (experimental, off by default): conv_decode1 and the 1x1 classifier as one 64 -> 16 convolution with
+    composed half weights (k_conv_tc_pair<7, true, 16>).  Same function up to half rounding of the weights / of the 64-channel
+    activation (tools/compose_classifier_study.py), so the maps agree statistically, not bitwise."""
+    net, w, proto, model = _full_model(model_dir)
+    left, _ = stereo_frame(5)
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SIVO_B200_COMPOSE", flag)
+        seg = BayesianSegNet(BayesianSegNetParams(proto, model), seed=1234, T=2, precision="fp16", engine="auto")
+        seg.set_frame(3)
+        outs.append(seg.segmentImage(left))
+    (c0, f0, e0), (c1, f1, e1) = outs
+    assert not np.array_equal(e0, e1), "the composed kernel did not engage"
+    assert (c0 != c1).mean() < 2e-3
+    assert np.median(np.abs(e0 - e1)) < 1e-3 and np.median(np.abs(f0 - f1)) < 1e-3
+    assert np.abs(f0 - f1).mean() < 5e-3
