@@ -47,18 +47,18 @@ def parse_args():
 def model_files(kind, T, cache_dir):
     """Prototxt + seeded synthetic caffemodel (the reference's weights are Git-LFS stubs)."""
     import gen_prototxt
-    from sivo_b200.caffemodel import write_synth_model
+    from sivo_b200.caffemodel import shipped_scales, write_synth_model
     from sivo_b200.prototxt import load_net
     os.makedirs(cache_dir, exist_ok=True)
     text = getattr(gen_prototxt, kind)(T=T)
     proto = os.path.join(cache_dir, f"{kind}_T{T}.prototxt")
-    model = os.path.join(cache_dir, f"{kind}_seed0.caffemodel")
+    model = os.path.join(cache_dir, f"{kind}_seed0_calibrated.caffemodel")
     with open(proto, "w") as f:
         f.write(text)
     net = load_net(text)
     weights = None
     if not os.path.exists(model):
-        weights = write_synth_model(net, model, 0)
+        weights = write_synth_model(net, model, 0, shipped_scales(kind))  # calibrated: O(1) activations, unsaturated softmax
     return net, proto, model, weights
 
 

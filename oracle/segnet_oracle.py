@@ -110,14 +110,18 @@ def mc_reduce(prob: np.ndarray):
 
 def forward(net, weights: Dict[str, List[np.ndarray]], image_bgr: np.ndarray, seed: int = 1234,
             frame: int = 0, precision: str = "fp32", T: Optional[int] = None, dedup: bool = True,
-            threads: Optional[int] = None, return_blobs: bool = False, masks: Optional[Dict[str, np.ndarray]] = None):
+            threads: Optional[int] = None, return_blobs: bool = False, masks: Optional[Dict[str, np.ndarray]] = None,
+            stop_after: Optional[str] = None):
     """Runs the net on one (already cropped or larger) BGR u8 image; returns prob [T,C,H,W] float32.
 
     `masks` (blob name -> Caffe-style plane index array) replaces the argmax decisions of the named pooling
     layers: the pooled value is gathered at the given index.  Tests use it to hand the oracle the device's
     tie-breaks -- two window entries that differ by <= 1 half ulp may legitimately swap order between two fp32
     summation orders, and one swapped position moves a whole activation under the next 7x7 filter -- so that
-    everything downstream can be compared tightly; the swapped positions themselves are checked to be such ties."""
+    everything downstream can be compared tightly; the swapped positions themselves are checked to be such ties.
+
+    `stop_after` (layer name) ends the pass after that layer and returns the blob dict so far (used by the synthetic-weight
+    calibration, tools/calibrate_synth.py)."""
     if threads:
         torch.set_num_threads(threads)
     T = T or net.T
@@ -199,6 +203,8 @@ def forward(net, weights: Dict[str, List[np.ndarray]], image_bgr: np.ndarray, se
                         del blobs[key]
                         if "Softmax" not in consumers.get(top, []):
                             blobs[top] = _h(blobs[top])
+            if stop_after is not None and ly.name == stop_after:
+                return {k: v for k, v in blobs.items() if not k.startswith("__")}
     prob = blobs[net.layers[-1].tops[0]]
     if prob.shape[0] == 1 and T > 1:
         prob = prob.repeat(T, 1, 1, 1)

@@ -143,10 +143,21 @@ def read_caffemodel(path: str) -> Dict[str, List[np.ndarray]]:
     return out
 
 
-def synth_weights(net: NetSpec, seed: int = 0) -> Dict[str, List[np.ndarray]]:
+def shipped_scales(kind: str) -> Dict[str, float]:
+    """The committed per-layer calibration factors of the two shipped topologies (configs/synth_scales.json, written by
+    tools/calibrate_synth.py): with them the seeded nets keep O(1) activations and logits of std ~2.5 at any input size."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "configs", "synth_scales.json")
+    return {k: float(v) for k, v in json.load(open(path))[kind].items()}
+
+
+def synth_weights(net: NetSpec, seed: int = 0, scales: Dict[str, float] = None) -> Dict[str, List[np.ndarray]]:
     """Seeded weights from the prototxt's fillers: `msra` = N(0, sqrt(2/fan_in)),
     `xavier` = U(+-sqrt(3/fan_in)) (caffe/include/caffe/filler.hpp); biases N(0, 0.1) and BN
-    scale 1+N(0,0.1), shift N(0,0.1) so that neither path is trivially the identity."""
+    scale 1+N(0,0.1), shift N(0,0.1) so that neither path is trivially the identity.
+    `scales` (conv layer name -> factor) multiplies that layer's weight and bias blobs: the calibration that keeps the
+    untrained net's activations O(1) and its softmax unsaturated (tools/calibrate_synth.py)."""
     rng = np.random.default_rng(seed)
     out: Dict[str, List[np.ndarray]] = {}
     ltypes = {ly.name: ly for ly in net.layers}
@@ -163,6 +174,8 @@ def synth_weights(net: NetSpec, seed: int = 0) -> Dict[str, List[np.ndarray]]:
             blobs = [w.astype(np.float32)]
             if len(shapes) > 1:
                 blobs.append(rng.normal(0.0, 0.1, size=shapes[1]).astype(np.float32))
+            if scales and name in scales:
+                blobs = [b * np.float32(scales[name]) for b in blobs]
             out[name] = blobs
         else:  # BN: blobs[0] = scale, blobs[1] = shift (caffe/src/caffe/layers/bn_layer.cpp:62-74)
             out[name] = [(1.0 + rng.normal(0.0, 0.1, size=shapes[0])).astype(np.float32),
@@ -170,7 +183,7 @@ def synth_weights(net: NetSpec, seed: int = 0) -> Dict[str, List[np.ndarray]]:
     return out
 
 
-def write_synth_model(net: NetSpec, path: str, seed: int = 0) -> Dict[str, List[np.ndarray]]:
-    w = synth_weights(net, seed)
+def write_synth_model(net: NetSpec, path: str, seed: int = 0, scales: Dict[str, float] = None) -> Dict[str, List[np.ndarray]]:
+    w = synth_weights(net, seed, scales)
     write_caffemodel(path, net.name, w, {ly.name: ly.type for ly in net.layers})
     return w

@@ -410,7 +410,21 @@ int sivo_dbg_conv(int device, int engine, int precision, const float* in, int n,
     SIVO_CUDA(cudaMemcpy(op.bn_shift.p, sh.data(), sh.size() * 4, cudaMemcpyHostToDevice));
     op.has_bn = bn_scale != nullptr;
     // tensors for the tc plan live in a scratch vector; run on the default stream
-    if (engine == SIVO_ENGINE_TCGEN05) {
+    if (engine == SIVO_ENGINE_TCGEN05 && dt == DType::F32) {  // split-operand fp32 mode
+      TensorView vs = vi;
+      vs.dt = DType::F16;
+      vs.cs = 2 * vi.cs;
+      op.split = true;
+      if (cin % 64 || !conv_tc_supported(op, vs, vo)) fail(SIVO_EINVAL, "conv: shape not supported by the split-operand tcgen05 mode");
+      std::vector<__half> wsplit = conv_tc_split_weights(weight, cout, cin, k, op.cout_p, op.cin_p, &op.acc_scale);
+      op.w_tc.alloc(wsplit.size() * 2);
+      SIVO_CUDA(cudaMemcpy(op.w_tc.p, wsplit.data(), wsplit.size() * 2, cudaMemcpyHostToDevice));
+      op.a_split.alloc(vs.elems() * 2);
+      vs.p = op.a_split.p;
+      op.tc = conv_tc_plan(op, vs, vo, op.w_tc.p);
+      launch_split_hilo(vi, op.a_split.p, nullptr);
+      conv_tc_launch(*op.tc, op, nullptr);
+    } else if (engine == SIVO_ENGINE_TCGEN05) {
       if (dt != DType::F16 || !conv_tc_supported(op, vi, vo)) fail(SIVO_EINVAL, "conv: shape not supported by the tcgen05 engine");
       op.tc = conv_tc_plan(op, vi, vo, op.w_tc.p);
       conv_tc_launch(*op.tc, op, nullptr);

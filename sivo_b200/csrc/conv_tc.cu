@@ -27,6 +27,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -53,7 +54,16 @@ struct TcParams {
   int dbg_noepi;           // timing experiment only: 1 = epilogue does nothing, 2 = TMEM loads only, 3 = no global stores
   int dbg_noshift;         // timing experiment only: ignore the kw shift of the A operand (wrong results)
   int b_stages;            // weight ring depth (as many of kMaxBStages as fit in shared memory)
-  int out_f32;             // 1: 16-channel float output (logits)
+  int out_f32;             // 1: 16-channel float output (logits); 2: n_tile-wide float output (split-operand fp32 mode)
+  int split;               // split-operand fp32 mode: A = [hi Cin | lo Cin] half planes of the float input, B K-axis = per real chunk
+                           // [W_hi | W_lo | W_hi]; `chunks` then counts A chunks (2 * Cin / 64: hi and lo of each, interleaved)
+  int cin_real;            // Cin (split mode: channel offset of the lo plane)
+  float acc_scale;         // split mode: the weights were scaled by a power of two before the hi/lo split; 1 / that
+  int seg_rows;            // split mode: tap rows per accumulation segment.  The tensor core adds into its fp32 accumulator with
+                           // truncation (measured: ~2^-25 relative per accumulate step, always towards zero, so it grows linearly
+                           // with the chain length: 1.4e-5 for a 7x7x64 layer); the block's MMAs are therefore cut into segments
+                           // of (A chunk, seg_rows tap rows) that each start a fresh accumulator, and the epilogue sums the
+                           // segments in registers with round-to-nearest adds.
   int pairs_per_cta;       // row blocks (R output rows each) one CTA walks
   int strips;              // ceil(W / 128)
   int relu, has_bn, has_drop;
@@ -225,7 +235,7 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, const TcConsts& 
     const int cl = lane & 3;          // this lane's 16-byte chunk after the transpose
     const int xg = x - cl;            // first pixel of the lane's group of four
     const bool row_ok = y < p.H;
-    if (p.out_f32) {  // 16-channel float logits (the convolution feeding Softmax)
+    if (p.out_f32 == 1) {  // 16-channel float logits (the convolution feeding Softmax)
       uint32_t v[32];
       tmem_ld16(trow, v);
       float4 e[4];
@@ -419,7 +429,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           const __grid_constant__ TcConsts cst) {
   asm volatile("griddepcontrol.launch_dependents;");  // the next kernel's CTAs may be scheduled as soon as all of ours have started
   constexpr int RK = kRows + K - 1;                  // halo rows one row pair reads (per chunk)
-  constexpr int kSlots = ROLL ? RK : 2 * RK;         // ROLL: rows are released as soon as their last tap row is issued
+  // rows are released as soon as their last tap row is issued; !ROLL double-buffers chunks where that fits (K = 7: RK + 2)
+  constexpr int kSlots = ROLL ? RK : (K == 7 ? RK + 2 : 2 * RK);
   constexpr int kPad = (K - 1) / 2, kPadW = (KW - 1) / 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -491,7 +502,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         }
         mbar_wait(a_empty + slot, (round & 1) ^ 1);
         mbar_expect_tx(a_full + slot, static_cast<uint32_t>((128 + KW - 1) * 128));
-        tma_load_4d(a_slots + slot * kSlotBytes, &map_a, a_full + slot, ch * 64, x0 - kPadW, yy, img);
+        const int a_ch = p.split ? (ch & 1) * p.cin_real + (ch >> 1) * 64 : ch * 64;  // split: chunk = (real chunk, hi | lo plane)
+        tma_load_4d(a_slots + slot * kSlotBytes, &map_a, a_full + slot, a_ch, x0 - kPadW, yy, img);
       }
     }
   } else if (warp == 1) {
@@ -501,13 +513,18 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       const int w_replica = static_cast<int>((blockIdx.x + blockIdx.z) % static_cast<unsigned>(p.w_rep));
       uint32_t it = 0;
       for (int j = 0; j < npairs; ++j)
-        for (int ch = 0; ch < NC; ++ch)
-          for (int tap = 0; tap < K * KW; ++tap, ++it) {
-            const int st = it % kBStages;
-            mbar_wait(b_empty + st, ((it / kBStages) & 1) ^ 1);
-            mbar_expect_tx(b_full + st, static_cast<uint32_t>(b_bytes));
-            tma_load_3d(b_stages + st * b_stride, &map_b, b_full + st, ch * 64, n0, tap + w_replica * K * KW);
-          }
+        for (int ch = 0; ch < NC; ++ch) {
+          // split: a hi chunk meets W_hi and W_lo (two tiles per tap), a lo chunk W_hi only; K-axis = [W_hi | W_lo | W_hi] per real chunk
+          const int nrep = p.split && !(ch & 1) ? 2 : 1;
+          for (int tap = 0; tap < K * KW; ++tap)
+            for (int rep = 0; rep < nrep; ++rep, ++it) {
+              const int st = it % kBStages;
+              mbar_wait(b_empty + st, ((it / kBStages) & 1) ^ 1);
+              mbar_expect_tx(b_full + st, static_cast<uint32_t>(b_bytes));
+              const int kc = p.split ? (3 * (ch >> 1) + ((ch & 1) ? 2 : rep)) * 64 : ch * 64;
+              tma_load_3d(b_stages + st * b_stride, &map_b, b_full + st, kc, n0, tap + w_replica * K * KW);
+            }
+        }
     }
   } else if (warp == 2 || warp == 3) {
     // ===== MMA issuers: warp 2 owns output rows [0, kRows/2), warp 3 the rest.  The loops are warp-uniform (all 32
@@ -521,13 +538,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     int st = 0;
     uint32_t b_phase = 0;
     int waited = 0;  // halo units whose TMA has been observed
+    int seg = 0;  // accumulation segments issued so far (== row blocks unless split mode cuts a block into several)
+    const int S = p.split ? p.seg_rows : K;
     for (int j = 0; j < npairs; ++j) {
-      const int acc = j & 1;
-      mbar_wait(t_empty + acc, ((j >> 1) & 1) ^ 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      int acc = seg & 1;
       for (int ch = 0; ch < NC; ++ch) {
         const int base_u = ROLL ? j * kRows : (j * NC + ch) * RK;
         for (int kh = 0; kh < K; ++kh) {
+          const bool seg_start = p.split ? (kh % S == 0) : (ch == 0 && kh == 0);
+          const bool seg_end = p.split ? (kh % S == S - 1 || kh == K - 1) : (ch == NC - 1 && kh == K - 1);
+          if (seg_start) {
+            acc = seg & 1;
+            mbar_wait(t_empty + acc, ((seg >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
           while (waited <= base_u + kh + kRows - 1 && waited < n_units) {
             mbar_wait(a_full + waited % kSlots, (waited / kSlots) & 1);
             ++waited;
@@ -540,10 +564,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             a_row_lo[m] = (((a_base + (unit % kSlots) * kSlotBytes) & 0x3FFFFu) >> 4) | (1u << 16);
             d_row[m] = tmem_base + static_cast<uint32_t>((acc * kRows + r_first + m) * p.n_tile);
           }
-          const uint32_t first_row = (ch | kh) ? 1u : 0u;
+          const uint32_t first_row = p.split ? (kh % S ? 1u : 0u) : ((ch | kh) ? 1u : 0u);  // 0: the segment's first MMAs clear
           const uint32_t kw_step = p.dbg_noshift ? 0u : 8u;
+          const int nrep = p.split && !(ch & 1) ? 2 : 1;
 #pragma unroll
-          for (int kw = 0; kw < KW; ++kw) {
+          for (int kw = 0; kw < KW; ++kw)
+          for (int rep = 0; rep < nrep; ++rep) {
             mbar_wait(b_full + st, b_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // descriptors: the high word is constant; the low word is (address >> 4) | LBO; a K step of 16 halfs
@@ -557,28 +583,32 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
                 for (int m = 0; m < kMine; ++m)
                   umma_f16(d_row[m], (static_cast<uint64_t>(kDescHi) << 32) | (a_row_lo[m] + kw_step * kw + 2 * k),
-                           (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k), idesc, first_row | static_cast<uint32_t>(kw | k));
+                           (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k), idesc, first_row | static_cast<uint32_t>(kw | k | rep));
               }
               umma_commit(b_empty + st);  // weight stage is free once both issuers' MMAs retire
             }
             __syncwarp();
             if (++st == kBStages) { st = 0; b_phase ^= 1; }
           }
-          // ROLL: halo row base_u + kh (kh < kRows) is only read by tap rows <= kh of this block and by no later
-          // block, so its slot goes back to the producer now and the next block's rows stream in behind the MMAs
-          if (ROLL && kh < kRows && elect_one()) umma_commit(a_empty + (base_u + kh) % kSlots);
+          // halo row base_u + kh is only read by tap rows <= kh of this block.  ROLL: rows >= kRows are also the next block's, so
+          // only kh < kRows goes back to the producer now (the next block's rows stream in behind the MMAs); !ROLL: every
+          // chunk fetches its own rows, so row kh is dead after tap row kh
+          if ((!ROLL || kh < kRows) && elect_one()) umma_commit(a_empty + (base_u + kh) % kSlots);
           __syncwarp();
+          if (seg_end) {
+            if (elect_one()) umma_commit(t_full + acc);
+            __syncwarp();
+            ++seg;
+          }
         }
         if (elect_one()) {
           if (ROLL && K < kRows)  // fewer tap rows than output rows: release the rest of this block's own rows
             for (int i = K; i < kRows; ++i) umma_commit(a_empty + (base_u + i) % kSlots);
-          if (!ROLL)  // this chunk's halo rows are dead
-            for (int i = 0; i < RK; ++i) umma_commit(a_empty + (base_u + i) % kSlots);
+          if (!ROLL)  // the chunk's remaining halo rows (last read by tap row K - 1) are dead
+            for (int i = K; i < RK; ++i) umma_commit(a_empty + (base_u + i) % kSlots);
         }
         __syncwarp();
       }
-      if (elect_one()) umma_commit(t_full + acc);
-      __syncwarp();
     }
   }
   } else {
@@ -590,6 +620,85 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int eset = (warp - 4) >> 2;  // 0: first half of the block's rows, 1: second half
     const int x = x0 + q * 32 + lane;
+    if (!ROLL && kRows == 2 && p.split) {
+      // split-operand fp32 mode: a block arrives as NC * ceil(K / seg_rows) accumulation segments; each epilogue warp owns one
+      // of the block's two rows, sums the segments in registers (round-to-nearest) and finishes the row after the last one
+      const int segs = NC * ((K + p.seg_rows - 1) / p.seg_rows);
+      const int y_row = eset;  // kRows == 2: set 0 takes row 0, set 1 row 1
+      int seg = 0;
+      for (int j = 0; j < npairs; ++j) {
+        float accr[128];
+#pragma unroll
+        for (int i = 0; i < 128; ++i) accr[i] = 0.f;
+        for (int sg = 0; sg < segs; ++sg, ++seg) {
+          const int acc = seg & 1;
+          mbar_wait(t_full + acc, (seg >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + y_row) * p.n_tile);
+          if (p.n_tile == 16) {
+            uint32_t v[32];
+            tmem_ld16(trow, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) accr[i] = __fadd_rn(accr[i], __uint_as_float(v[i]));
+          } else {
+#pragma unroll
+            for (int cc = 0; cc < 128; cc += 32)
+              if (cc < p.n_tile) {
+                uint32_t v[32];
+                tmem_ld32(trow + cc, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) accr[cc + i] = __fadd_rn(accr[cc + i], __uint_as_float(v[i]));
+              }
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty + acc);
+        }
+        // finish the row: x 2^-s, bias, BN affine, ReLU in fp32 (as the reference), float NHWC store (4-lane transposed)
+        const int y = y_base + j * kRows + y_row;
+        const bool row_ok = y < p.H;
+        const int cl = lane & 3, xg = x - cl;
+        if (p.n_tile == 16) {
+          float4 e[4];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float t = __fadd_rn(__fmul_rn(accr[i], p.acc_scale), cst.bias[i]);
+            if (p.has_bn) t = __fadd_rn(__fmul_rn(t, cst.bn_scale[i]), cst.bn_shift[i]);
+            if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
+            reinterpret_cast<float*>(&e[i >> 2])[i & 3] = t;
+          }
+          quad_transpose(e, lane);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            if (row_ok && xg + jj < p.W)
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ((static_cast<size_t>(img) * p.H + y) * p.W + xg + jj) * 16 + 4 * cl) = e[jj];
+        } else {
+#pragma unroll
+          for (int cc = 0; cc < 128; cc += 32)
+            if (cc < p.n_tile) {
+              const int c0 = n0 + cc;
+              float4 ea[4], eb[4];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float t = __fadd_rn(__fmul_rn(accr[cc + i], p.acc_scale), cst.bias[c0 + i]);
+                if (p.has_bn) t = __fadd_rn(__fmul_rn(t, cst.bn_scale[c0 + i]), cst.bn_shift[c0 + i]);
+                if (p.relu) t = t > 0.f ? t : __fmul_rn(p.slope, t);
+                if (i < 16) reinterpret_cast<float*>(&ea[i >> 2])[i & 3] = t;
+                else reinterpret_cast<float*>(&eb[(i - 16) >> 2])[i & 3] = t;
+              }
+              quad_transpose(ea, lane);  // ea[jj] = channels [c0 + 4 cl, +4) of pixel xg + jj; eb the same 16 channels further
+              quad_transpose(eb, lane);
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                if (row_ok && xg + jj < p.W) {
+                  float* o = reinterpret_cast<float*>(p.out) + ((static_cast<size_t>(img) * p.H + y) * p.W + xg + jj) * p.cout_total + c0 + 4 * cl;
+                  *reinterpret_cast<float4*>(o) = ea[jj];
+                  *reinterpret_cast<float4*>(o + 16) = eb[jj];
+                }
+            }
+        }
+      }
+    } else
     for (int j = 0; j < npairs; ++j) {
       const int acc = j & 1;
       mbar_wait(t_full + acc, (j >> 1) & 1);
@@ -936,7 +1045,7 @@ void conv_tc_dispatch(const ConvTcPlan& plan, cudaStream_t s, bool configure) {
   }
   else if (plan.roll && plan.rows == 4) { if (K == 7) go(k_conv_tc<7, true, 4>); else if (K == 3) go(k_conv_tc<3, true, 4>); else go(k_conv_tc<1, true, 4>); }
   else if (plan.roll) { if (K == 7) go(k_conv_tc<7, true, 2>); else if (K == 3) go(k_conv_tc<3, true, 2>); else go(k_conv_tc<1, true, 2>); }
-  else { if (K == 3) go(k_conv_tc<3, false, 2>); else go(k_conv_tc<1, false, 2>); }
+  else { if (K == 7) go(k_conv_tc<7, false, 2>); else if (K == 3) go(k_conv_tc<3, false, 2>); else go(k_conv_tc<1, false, 2>); }
 }
 }  // namespace
 
@@ -950,7 +1059,7 @@ int tc_rows(int K, bool roll, int n_tile, int columns = 1 << 30, int H = 1 << 20
 size_t tc_smem_bytes(int K, bool roll, int n_tile, int stages) {
   const int rows = tc_rows(K, roll, n_tile);  // the 4-row variant is the larger footprint
   const int rk = rows + K - 1;
-  const int slots = roll ? rk : 2 * rk;
+  const int slots = roll ? rk : (K == 7 ? rk + 2 : 2 * rk);  // k_conv_tc's kSlots
   const int b_stride = (n_tile * 128 + 1023) & ~1023;
   return 1024 + static_cast<size_t>(slots) * kSlotBytes + static_cast<size_t>(stages) * b_stride + (2 * slots + 2 * stages + 4) * 8 + 16 + 64 * 16 * 4;  // barriers, TMEM slot, fused-classifier weights
 }
@@ -960,7 +1069,7 @@ int tc_stages(int K, bool roll, int n_tile) {  // deepest weight ring that fits 
   return 0;
 }
 int tc_pick_n(const Op& op, const TensorView& out, bool roll) {
-  if (out.dt == DType::F32) return 16;
+  if (out.dt == DType::F32 && out.cs <= 16) return 16;  // the float logits layer
   int n = (op.cout_p % 128 == 0) ? 128 : 64;
   if (!tc_stages(op.k, roll, n)) n = 64;
   return n;
@@ -976,6 +1085,11 @@ bool conv_tc_supported(const Op& op, const TensorView& in, const TensorView& out
     if (in.cs != 8 || op.cin_p != 64 || (op.k != 3 && op.k != 7) || out.dt != DType::F16 || op.cout % 64 || out.cs != op.cout) return false;
     return tc_stages(op.k, true, tc_pick_n(op, out, true)) > 0;
   }
+  if (op.split) {  // `in` = the [hi Cin | lo Cin] half planes of the float input
+    if (op.cin % 64 || in.cs != 2 * op.cin || out.dt != DType::F32) return false;
+    if (!((out.cs == op.cout && op.cout % 64 == 0) || (out.cs == 16 && op.cout <= 16))) return false;
+    return tc_stages(op.k, false, tc_pick_n(op, out, false)) > 0;
+  }
   if (in.cs % 64 || op.cin != in.cs) return false;
   if (out.dt == DType::F16) {
     if (op.cout % 64 || out.cs != op.cout) return false;
@@ -990,7 +1104,7 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   auto plan = std::make_shared<ConvTcPlan>();
   const int K = op.k;
   const int KW = op.fold_kw ? 1 : K;
-  const bool roll = in.cs == 64 || op.fold_kw;
+  const bool roll = (in.cs == 64 || op.fold_kw) && !op.split;
   if (op.fold_kw) {
     // window-folded input: `in` is the zero-padded 8-channel image [N][H][W + 8][8] half (3 zero pixels left, 5 right);
     // "pixel" x of the operand is the 128-byte window of 8 pixels x 8 channels starting at padded pixel x, i.e. image
@@ -1014,7 +1128,7 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   int w_rep = 1;
   if (const char* e = std::getenv("SIVO_B200_TC_WREP")) w_rep = std::max(1, std::min(16, atoi(e)));
   {  // weights: [replica][tap][cout_p][cin_p] half, dims (cin, cout, replica * tap)
-    const size_t one = static_cast<size_t>(K) * KW * op.cout_p * op.cin_p * 2;
+    const size_t one = static_cast<size_t>(K) * KW * op.cout_p * op.cin_p * 2 * (op.split ? 3 : 1);
     void* wbase = const_cast<void*>(w_tc);
     if (w_rep > 1) {
       plan->w_replicas.alloc(one * w_rep);
@@ -1022,8 +1136,9 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
         SIVO_CUDA(cudaMemcpy(plan->w_replicas.as<uint8_t>() + r * one, w_tc, one, cudaMemcpyDeviceToDevice));
       wbase = plan->w_replicas.p;
     }
-    cuuint64_t dims[3] = {static_cast<cuuint64_t>(op.cin_p), static_cast<cuuint64_t>(op.cout_p), static_cast<cuuint64_t>(K * KW * w_rep)};
-    cuuint64_t strides[2] = {static_cast<cuuint64_t>(op.cin_p) * 2, static_cast<cuuint64_t>(op.cout_p) * op.cin_p * 2};
+    const int kext = op.split ? 3 * op.cin_p : op.cin_p;  // split: [W_hi | W_lo | W_hi] per 64-channel chunk along K
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(kext), static_cast<cuuint64_t>(op.cout_p), static_cast<cuuint64_t>(K * KW * w_rep)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(kext) * 2, static_cast<cuuint64_t>(op.cout_p) * kext * 2};
     cuuint32_t box[3] = {64, static_cast<cuuint32_t>(n_tile), 1};
     encode(&plan->map_b, wbase, 3, dims, strides, box);
   }
@@ -1033,9 +1148,14 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   p.n_tile = n_tile;
   p.chunks = op.fold_kw ? 1 : in.cs / 64;
   p.w_rep = w_rep;
-  p.out_f32 = out.dt == DType::F32;
+  p.out_f32 = out.dt == DType::F32 ? (n_tile == 16 ? 1 : 2) : 0;
+  p.split = op.split ? 1 : 0;
+  p.cin_real = op.cin;
+  p.acc_scale = op.split ? op.acc_scale : 1.f;
+  p.seg_rows = K == 7 ? 1 : K;  // 7x7: a segment per (chunk, tap row) = 56 / 28 accumulate steps; 3x3 / 1x1: per chunk (72 / 36, 8 / 4)
+  if (const char* e = std::getenv("SIVO_B200_SPLIT_SEG")) p.seg_rows = std::max(1, std::min(K, atoi(e)));
   p.strips = ceil_div(p.W, 128);
-  const int cout_tiles = p.out_f32 ? 1 : op.cout_p / n_tile;
+  const int cout_tiles = p.out_f32 == 1 ? 1 : op.cout_p / n_tile;
   const int columns = p.strips * in.n * cout_tiles;
   const int rows = tc_rows(K, roll, n_tile, columns, in.h);
   const int total_pairs = ceil_div(in.h, rows);
@@ -1103,7 +1223,6 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   plan->kw = KW;
   plan->roll = roll;
   plan->rows = rows;
-  if (!roll && K == 7) fail(SIVO_EINVAL, "7x7 with Cin > 64 is not built");
   conv_tc_dispatch(*plan, nullptr, true);
   return plan;
 }
@@ -1132,6 +1251,30 @@ std::vector<__half> conv_tc_pair_weights(const float* w_cout_cin_k_k, int K) {
           out[((static_cast<size_t>(kw) * K + kh) * 64 + co) * 64 + ci] =
               __float2half_rn(w_cout_cin_k_k[((static_cast<size_t>(co) * 64 + ci) * K + kh) * K + kw]);
   return out;
+}
+
+std::vector<__half> conv_tc_split_weights(const float* W, int cout, int cin, int K, int cout_p, int cin_p, float* acc_scale) {
+  // [tap][cout_p][3 cin_p] half: per 64-channel chunk c of the K axis [W_hi(c) | W_lo(c) | W_hi(c)], where W * 2^s = W_hi + W_lo.
+  // The power-of-two scale lifts the low parts out of half's subnormal range (|w| ~ 1e-2 has ulp(hi) ~ 2^-17 < 2^-14); the
+  // epilogue multiplies the accumulator by 2^-s, which is exact.
+  float wmax = 0.f;
+  for (size_t i = 0; i < static_cast<size_t>(cout) * cin * K * K; ++i) wmax = std::max(wmax, std::fabs(W[i]));
+  int e = 0;
+  if (wmax > 0.f && std::isfinite(wmax)) { std::frexp(wmax, &e); e = 8 - e; }  // wmax * 2^e in [128, 256)
+  e = std::max(-24, std::min(24, e));
+  const float up = std::ldexp(1.f, e);
+  *acc_scale = std::ldexp(1.f, -e);
+  const int kext = 3 * cin_p;
+  std::vector<__half> wt(static_cast<size_t>(K) * K * cout_p * kext, __float2half_rn(0.f));
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int t = 0; t < K * K; ++t) {
+        const float v = W[(static_cast<size_t>(co) * cin + ci) * K * K + t] * up;
+        const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
+        __half* row = wt.data() + (static_cast<size_t>(t) * cout_p + co) * kext + (ci / 64) * 192 + ci % 64;
+        row[0] = hi; row[64] = lo; row[128] = hi;
+      }
+  return wt;
 }
 
 bool conv_tc_can_fuse_pool(const ConvTcPlan& plan) {

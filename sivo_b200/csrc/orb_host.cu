@@ -344,6 +344,9 @@ void Orb::ensure(int rows, int cols) {
     level_size(rows, cols, l, &lv.w, &lv.h);
     if (lv.w < 2 * kEdge + 7 || lv.h < 2 * kEdge + 7)
       fail(SIVO_EINVAL, "image %dx%d is too small for %d pyramid levels", cols, rows, nlevels_);
+    // FAST candidates are packed x:12 | y:12 | response:8 (k_cells): larger levels would wrap silently
+    if (lv.w + 2 * kEdge > 4096 || lv.h + 2 * kEdge > 4096)
+      fail(SIVO_EINVAL, "image %dx%d exceeds the extractor's 4096-pixel candidate packing", cols, rows);
     lv.pitch = (lv.w + 2 * kEdge + 15) / 16 * 16;
     lv.img_off = img_off;
     lv.flat_off = flat_off;

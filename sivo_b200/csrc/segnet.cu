@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -78,6 +79,12 @@ void SegNet::prepare_conv(Op& op, const std::vector<Blob>& cb, const std::vector
       SIVO_CUDA(cudaMemcpy(op.w_tc_pair.p, wp.data(), wp.size() * sizeof(__half), cudaMemcpyHostToDevice));
     }
   }
+  if (op.split) {
+    if (taps != K * K) fail(SIVO_EINVAL, "layer '%s': split-operand mode does not take folded / expanded first layers", op.layer.c_str());
+    std::vector<__half> wt = conv_tc_split_weights(W, cout, cin, K, op.cout_p, op.cin_p, &op.acc_scale);
+    op.w_tc.alloc(wt.size() * sizeof(__half));
+    SIVO_CUDA(cudaMemcpy(op.w_tc.p, wt.data(), wt.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  }
   std::vector<float> b(op.cout_p, 0.f);
   if (cb.size() > 1) {
     if (static_cast<int>(cb[1].count()) != cout) fail(SIVO_EFORMAT, "layer '%s': bias blob size mismatch", op.layer.c_str());
@@ -121,6 +128,10 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
   auto blob_id = [&](const std::string& name) {
     auto it = by_name_.find(name);
     if (it == by_name_.end()) fail(SIVO_EFORMAT, "prototxt: blob '%s' is used before it is produced", name.c_str());
+    // a fused kernel consumes this blob in registers and never writes it: a second consumer would read uninitialised memory
+    if (tensors_[it->second]->elided)
+      fail(SIVO_EFORMAT, "prototxt: blob '%s' has more than one consumer; the fused pool / unpool / dropout / classifier paths need a "
+                         "single-consumer chain (create the net with keep_blobs to run it unfused)", name.c_str());
     return it->second;
   };
   int drop_idx = 0;
@@ -214,6 +225,15 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
         op.out = add_tensor(ly.tops[0], iv.n, op.cout, iv.h, iv.w, cs, logits ? DType::F32 : act_);
         auto it = weights.find(ly.name);
         if (it == weights.end()) fail(SIVO_EFORMAT, "caffemodel has no blobs for layer '%s'", ly.name.c_str());
+        // fp32 activations on the tensor-core engine: split-operand mode (three half MMAs per tap, fp32 accumulation)
+        TensorView split_in = civ;
+        if (act_ == DType::F32 && opt_.engine != SIVO_ENGINE_SIMT && !op.fold_kw && !op.expand_k && civ.cs % 64 == 0 && civ.c == civ.cs &&
+            !(no_tc && no_tc[0] == '1')) {
+          split_in.dt = DType::F16;
+          split_in.cs = 2 * civ.cs;
+          op.split = true;
+          if (!conv_tc_supported(op, split_in, tensors_[op.out]->v)) op.split = false;
+        }
         prepare_conv(op, it->second, bn);
         op.flops = 2.0 * iv.c * ly.kernel * ly.kernel * op.cout * iv.h * iv.w * iv.n;  // algorithmic, whatever the mapping
         flops_dedup += op.flops;
@@ -236,13 +256,18 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
           li = lj - 1;
           break;
         }
-        if (opt_.engine != SIVO_ENGINE_SIMT && act_ == DType::F16 &&
+        if (op.split) {
+          op.a_split.alloc(split_in.elems() * sizeof(__half));
+          split_in.p = op.a_split.p;
+          op.tc = conv_tc_plan(op, split_in, tensors_[op.out]->v, op.w_tc.p);
+          op.use_tc = true;
+        } else if (opt_.engine != SIVO_ENGINE_SIMT && act_ == DType::F16 &&
             conv_tc_supported(op, civ, tensors_[op.out]->v)) {
           op.tc = conv_tc_plan(op, civ, tensors_[op.out]->v, op.w_tc.p);
           op.use_tc = true;
         } else if (op.fold_kw) {
           fail(SIVO_EINVAL, "layer '%s': window-folded first layer is not supported by the tensor-core kernel", ly.name.c_str());
-        } else if (opt_.engine == SIVO_ENGINE_TCGEN05 && op.cin_p % 64 == 0 && !logits) {
+        } else if (opt_.engine == SIVO_ENGINE_TCGEN05 && op.cin_p % 64 == 0 && (!logits || act_ == DType::F32)) {
           fail(SIVO_EINVAL, "layer '%s': tcgen05 engine requested but the shape is not supported", ly.name.c_str());
         }
         ops_.push_back(std::move(op));
@@ -364,15 +389,18 @@ SegNet::SegNet(const std::string& prototxt, const std::string& caffemodel, const
   W_ = net.dims[3];
   if (H_ <= 0 || W_ <= 0) fail(SIVO_EFORMAT, "prototxt: bad input geometry %dx%d", W_, H_);
   act_ = opt.precision == SIVO_PRECISION_FP32 ? DType::F32 : DType::F16;
-  if (opt.precision == SIVO_PRECISION_FP32 && opt.engine == SIVO_ENGINE_TCGEN05)
-    fail(SIVO_EINVAL, "the tcgen05 engine computes on fp16 operands; fp32 precision needs the SIMT engine");
   WeightMap weights = read_caffemodel(caffemodel);
   device_ = opt.device;
   SIVO_CUDA(cudaSetDevice(device_));
   SIVO_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-  d_frame_.alloc(sizeof(uint64_t));
-  h_frame_.ensure(sizeof(uint64_t));
-  build(net, weights);
+  try {  // a malformed model throws out of build(): the destructor does not run for a half-built object
+    d_frame_.alloc(sizeof(uint64_t));
+    build(net, weights);
+  } catch (...) {
+    cudaStreamDestroy(stream_);
+    stream_ = nullptr;
+    throw;
+  }
   const size_t hw = static_cast<size_t>(H_) * W_;
   d_bgr_.alloc(hw * 3);
   d_classes_.alloc(hw);
@@ -415,6 +443,10 @@ void SegNet::enqueue(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_
         break;
       case Op::Conv: {
         if (op.use_tc) {
+          if (op.split) {  // the float input as [hi | lo] half planes
+            launch_split_hilo(tensors_[op.in]->v, op.a_split.p, s);
+            ++launches;
+          }
           conv_tc_launch(*op.tc, op, s);
         } else {
           ConvParams p;
@@ -506,8 +538,8 @@ void SegNet::run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* co
   SIVO_CUDA(cudaSetDevice(device_));
   if (!s) s = stream_;
   last_classes_ = classes_dev; last_conf_ = conf_dev; last_ent_ = ent_dev; last_stream_ = s;
-  *h_frame_.as<uint64_t>() = frame_++;
-  SIVO_CUDA(cudaMemcpyAsync(d_frame_.p, h_frame_.p, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  // by value, outside the captured graph: pipelined callers may issue the next frame before this one has started
+  launch_set_u64(d_frame_.as<uint64_t>(), frame_++, s);
   if (profiling_) {
     while (events_.size() < ops_.size() + 1) {
       cudaEvent_t e;

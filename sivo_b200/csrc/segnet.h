@@ -41,6 +41,12 @@ struct Op {
   bool relu = false, has_bn = false;
   float slope = 0.f;
   DevBuf w_simt, w_tc, w_tc_pair, bias, bn_scale, bn_shift;  // w_tc_pair: [kw][kh][cout][cin] half for the paired-tap kernel
+  // split-operand fp32 mode (precision fp32 on the tcgen05 engine): x = hi + lo and w * 2^s = hi + lo in half, and
+  // x * w ~= (x_hi w_hi + x_hi w_lo + x_lo w_hi) * 2^-s accumulated in fp32 -- three MMAs per tap, ~2^-22 relative per product.
+  // w_tc holds [tap][cout_p][3 cin_p] = per 64-channel chunk [W_hi | W_lo | W_hi]; a_split the [hi Cin | lo Cin] planes of the input.
+  bool split = false;
+  float acc_scale = 1.f;
+  DevBuf a_split;
   std::shared_ptr<ConvTcPlan> tc;
   bool use_tc = false;
   double flops = 0;  // algorithmic, for this op's batch
@@ -88,7 +94,7 @@ class SegNet {
   std::vector<Op> fused_;  // ops folded into a neighbour's epilogue; kept alive for their weight buffers
   cudaStream_t stream_ = nullptr;
   DevBuf d_bgr_, d_classes_, d_conf_, d_ent_, d_frame_;
-  PinnedBuf h_in_, h_classes_, h_conf_, h_ent_, h_frame_;
+  PinnedBuf h_in_, h_classes_, h_conf_, h_ent_;
   // where the last run left its maps on the device, and the stream it ran on (semantic_keys reads them)
   const uint8_t* last_classes_ = nullptr;
   const double* last_conf_ = nullptr;
@@ -124,6 +130,8 @@ bool conv_tc_can_fuse_pool(const ConvTcPlan& plan);
 void conv_tc_set_pool(ConvTcPlan& plan, void* pooled, uint8_t* mask);
 // fuses a following 1x1 convolution to <= 16 float logits (the layer feeding Softmax) into the epilogue
 bool conv_tc_can_fuse_classifier(const ConvTcPlan& plan);
+// host-side weight layout of the split-operand fp32 mode: [tap][cout_p][3 cin_p] half + the accumulator scale 2^-s
+std::vector<__half> conv_tc_split_weights(const float* w_cout_cin_k_k, int cout, int cin, int K, int cout_p, int cin_p, float* acc_scale);
 // host-side weight layout of the paired-tap kernel (64 -> 64 channels)
 std::vector<__half> conv_tc_pair_weights(const float* w_cout_cin_k_k, int K);
 // Experimental (SIVO_B200_COMPOSE=1): conv (64 -> 64, 7x7, no BN / ReLU) followed by the 1x1 classifier run as ONE 64 -> 16

@@ -644,6 +644,45 @@ void launch_input_lrn_pad8(const uint8_t* bgr, TensorView out, int size, float a
   SIVO_CUDA(cudaGetLastError());
 }
 
+// Split-operand fp32 mode: float NHWC [px][C] -> half [px][hi C | lo C] with hi = half(x), lo = half(x - hi) (both roundings
+// to nearest; x - hi is exact in fp32), the A operand planes of the tcgen05 convolution (conv_tc.cu, TcParams::split).
+__global__ void k_split_hilo(const float4* __restrict__ in, uint2* __restrict__ out, size_t npix, int c4) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= npix * c4) return;
+  const size_t px = i / c4;
+  const int q = static_cast<int>(i % c4);
+  const float4 v = __ldg(in + i);
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  __half hi[4], lo[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    hi[k] = __float2half_rn(f[k]);
+    lo[k] = __float2half_rn(__fsub_rn(f[k], __half2float(hi[k])));
+  }
+  auto pack = [](const __half* h) {
+    return make_uint2(static_cast<uint32_t>(__half_as_ushort(h[0])) | (static_cast<uint32_t>(__half_as_ushort(h[1])) << 16),
+                      static_cast<uint32_t>(__half_as_ushort(h[2])) | (static_cast<uint32_t>(__half_as_ushort(h[3])) << 16));
+  };
+  out[px * 2 * c4 + q] = pack(hi);
+  out[px * 2 * c4 + c4 + q] = pack(lo);
+}
+
+// The frame counter the dropout kernels read travels as a kernel argument (by value): an asynchronous copy from a single
+// pinned slot could be overwritten by the next run_device() before it executes, giving two frames the same masks.
+__global__ void k_set_u64(uint64_t* dst, uint64_t v) { *dst = v; }
+void launch_set_u64(uint64_t* dst, uint64_t v, cudaStream_t s) {
+  k_set_u64<<<1, 1, 0, s>>>(dst, v);
+  SIVO_CUDA(cudaGetLastError());
+}
+
+void launch_split_hilo(TensorView in, void* out_half, cudaStream_t s) {
+  if (in.dt != DType::F32 || in.cs % 4) fail(SIVO_EINVAL, "split_hilo: expects a float tensor with a channel stride that is a multiple of 4");
+  const size_t npix = static_cast<size_t>(in.n) * in.h * in.w;
+  const int c4 = in.cs / 4;
+  k_split_hilo<<<blocks_for(npix * c4, 256), 256, 0, s>>>(static_cast<const float4*>(in.p), static_cast<uint2*>(out_half), npix, c4);
+  SIVO_CUDA(cudaGetLastError());
+}
+
 void launch_pool(TensorView in, TensorView out, uint8_t* mask, cudaStream_t s) {
   size_t total = out.elems();
   DISPATCH_AT(in.dt, (k_pool<AT><<<blocks_for(total, 256), 256, 0, s>>>(static_cast<const AT*>(in.p), static_cast<AT*>(out.p),

@@ -50,6 +50,10 @@ void launch_keypoint_lookup(const sivo_keypoint* kps, int n, const uint8_t* clas
 void launch_pad8(TensorView in, TensorView out, cudaStream_t s);
 // the three steps input_u8 -> lrn -> pad8 in one pass (same arithmetic, so the same half values)
 void launch_input_lrn_pad8(const uint8_t* bgr, TensorView out, int size, float alpha, float beta, float k, cudaStream_t s);
+// float [px][C] -> half [px][hi C | lo C] (split-operand fp32 mode of the tensor-core convolution)
+void launch_split_hilo(TensorView in, void* out_half, cudaStream_t s);
+// *dst = v on stream s, the value passed as a kernel argument
+void launch_set_u64(uint64_t* dst, uint64_t v, cudaStream_t s);
 void launch_pool(TensorView in, TensorView out, uint8_t* mask, cudaStream_t s);
 // mask_n: batch of the mask tensor (1 when the pool ran in the sample-invariant prefix)
 void launch_unpool(TensorView in, const uint8_t* mask, int mask_n, TensorView out, cudaStream_t s);

@@ -114,10 +114,14 @@ def test_conv_simt_matches_oracle(k, cin, cout, prec):
 @pytest.mark.parametrize("k,cin,cout,n,h,w", [(7, 64, 64, 1, 8, 128), (7, 64, 64, 2, 22, 200), (3, 64, 64, 1, 16, 128),
                                               (3, 64, 128, 2, 11, 96), (7, 64, 64, 3, 44, 128), (3, 64, 64, 1, 64, 300),
                                               (1, 64, 15, 2, 10, 140), (3, 64, 15, 1, 12, 128), (3, 128, 128, 2, 11, 96),
-                                              (3, 256, 64, 1, 22, 64), (3, 512, 512, 2, 11, 32), (1, 128, 64, 1, 6, 130)])
+                                              (3, 256, 64, 1, 22, 64), (3, 512, 512, 2, 11, 32), (1, 128, 64, 1, 6, 130),
+                                              # 4-row blocks (columns x ceil(H/4) >= 148): the paired / TRIPLE stacked-tap kernels
+                                              (7, 64, 64, 2, 176, 512), (7, 64, 64, 1, 352, 300), (3, 64, 64, 1, 160, 512),
+                                              (3, 64, 64, 2, 90, 520)])
 def test_conv_tcgen05_matches_oracle(k, cin, cout, n, h, w):
     """The tensor-core convolution against torch fp32 on identical half-rounded operands; sizes cover partial
-    strips (W not a multiple of 128), an odd height, several images and both UMMA N tiles."""
+    strips (W not a multiple of 128), an odd height, several images, both UMMA N tiles, and shapes large enough to take the
+    4-row paired-tap (K = 3) and paired + TRIPLE stacked-tap (K = 7) kernels the full-size nets run."""
     import torch.nn.functional as F
     rng = np.random.default_rng(5)
     x = rng.normal(0, 1, size=(n, cin, h, w)).astype(np.float32)
@@ -134,3 +138,31 @@ def test_conv_tcgen05_matches_oracle(k, cin, cout, n, h, w):
     ref = (ref.half().float() if cout % 8 == 0 else ref).numpy()  # the 15-channel logits layer stays float
     err = np.abs(out - ref)
     assert err.max() < 2e-3 * max(1.0, float(np.abs(ref).max())), float(err.max())
+
+
+@pytest.mark.parametrize("k,cin,cout,n,h,w", [(7, 64, 64, 2, 22, 200), (3, 64, 64, 1, 16, 128), (3, 64, 128, 2, 11, 96),
+                                              (1, 64, 15, 2, 10, 140), (3, 64, 15, 1, 12, 128), (3, 128, 128, 2, 11, 96),
+                                              (3, 256, 64, 1, 22, 64), (3, 512, 512, 2, 11, 32), (7, 64, 64, 1, 60, 300)])
+def test_conv_tcgen05_split_operand_mode_is_fp32_grade(k, cin, cout, n, h, w):
+    """precision fp32 on the tcgen05 engine: x = hi + lo, w = hi + lo in half, x*w ~ hi*hi + hi*lo + lo*hi accumulated in fp32
+    (TMEM).  Compared with a float64 convolution of the same fp32 inputs; the bar is caffe's own conv tolerance (1e-4,
+    test_convolution_layer.cpp) with two orders of margin, and torch's fp32 convolution is measured next to it."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(6)
+    x = rng.normal(0, 1, size=(n, cin, h, w)).astype(np.float32)
+    wt = (rng.normal(0, 1, size=(cout, cin, k, k)) / np.sqrt(cin * k * k)).astype(np.float32)
+    b = rng.normal(0, 0.1, size=cout).astype(np.float32)
+    sc = (1 + rng.normal(0, 0.1, size=cout)).astype(np.float32)
+    sh = rng.normal(0, 0.1, size=cout).astype(np.float32)
+    out = np.empty((n, cout, h, w), np.float32)
+    L.check(L.lib().sivo_dbg_conv(0, L.ENGINE_TCGEN05, L.PRECISION_FP32, _p(x), n, cin, h, w, _p(wt), _p(b), _p(sc), _p(sh), cout,
+                                  k, (k - 1) // 2, 1, _p(out)))
+    xd, wd = torch.from_numpy(x).double(), torch.from_numpy(wt).double()
+    ref = F.conv2d(xd, wd, None, padding=(k - 1) // 2) + torch.from_numpy(b).double().view(1, -1, 1, 1)
+    ref = torch.relu(ref * torch.from_numpy(sc).double().view(1, -1, 1, 1) + torch.from_numpy(sh).double().view(1, -1, 1, 1)).numpy()
+    r32 = F.conv2d(torch.from_numpy(x), torch.from_numpy(wt), None, padding=(k - 1) // 2) + torch.from_numpy(b).view(1, -1, 1, 1)
+    r32 = torch.relu(r32 * torch.from_numpy(sc).view(1, -1, 1, 1) + torch.from_numpy(sh).view(1, -1, 1, 1)).numpy()
+    scale = max(1.0, float(np.abs(ref).max()))
+    err, err32 = float(np.abs(out - ref).max()) / scale, float(np.abs(r32 - ref).max()) / scale
+    print(f"split conv k={k} {cin}->{cout}: max err {err:.2e} of scale (torch fp32: {err32:.2e})")
+    assert err < 1e-5, err
