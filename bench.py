@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sustain-seconds", type=float, default=3.0,
+                    help="extra sustained leg on rank 0 (N=1): frames back to back for this long, own clock samples (0 = skip)")
     return ap.parse_args()
 
 
@@ -226,8 +228,10 @@ def workload_config(args, T):
                         f"(centre-cropped to 1024x352), one frame per GPU",
             "model": args.model, "T": T, "nfeatures": args.nfeatures, "engine": args.engine, "precision": args.precision,
             "l2": "inputs+activations per frame (>300 MB) exceed the 126 MB L2; distinct frame each step",
-            "calls": "per frame: segmentImage + the two ORBextractor calls, issued concurrently from three host threads "
-                     "(value: run_device graph replay + two run_device_input threads)"}
+            "calls": "value: run_device (graph replay) + the two extractors on two host threads, inputs resident in HBM.  "
+                     "e2e: the reference's call order -- segmentImage(host image) returns, THEN the two ORBextractor calls on two "
+                     "threads (src/orbslam/Frame.cc:125-129), page-locked caller buffers; e2e_variants holds the same with the three "
+                     "calls issued concurrently (one-line Frame.cc change, INTEGRATION.md) and with pageable caller buffers"}
 
 
 def main():
@@ -369,15 +373,35 @@ def main():
     pyr_t = [[torch.empty(shp, dtype=torch.uint8).pin_memory() for shp in orb_l.level_shapes(NET_H, NET_W)] for _ in range(2)]
     pyr_np = [[t.numpy() for t in lst] for lst in pyr_t]
 
-    def host_step(i):
+    # pageable twins of the e2e buffers: what the untouched shim hands over (Eigen / cv::Mat storage, integration/src)
+    h_fr_pageable = [tuple(np.array(a, copy=True) for a in f) for f in h_fr]
+    out_pageable = tuple(np.empty_like(a) for a in out_np)
+    pyr_pageable = [[np.empty_like(a) for a in lst] for lst in pyr_np]
+
+    def host_step(i, order="reference", pinned=True):
+        """One frame through the reference-facing calls on HOST buffers; each call is synchronous for its caller (host image in,
+        host results out, copies inside).  order "reference": segmentImage returns before the two extractor threads start
+        (src/orbslam/Frame.cc:125-129); "concurrent": the three independent calls are issued together."""
         j = i % n_frames
-        left, gl, gr = h_fr[j]
-        # the three operator calls of a frame are independent (the reference runs the two extractors on two threads,
-        # src/orbslam/Frame.cc:126-129); each call is synchronous for its caller: host image in, host results out, copies inside
-        fl_ = pool.submit(orb_l, gl, None, want_pyramid=True, pyramid_buffers=pyr_np[0])
-        fr_ = pool.submit(orb_r, gr, None, want_pyramid=True, pyramid_buffers=pyr_np[1])
-        res = seg.segmentImage(left, out=out_np)
-        return res, [fl_.result(), fr_.result()]
+        left, gl, gr = (h_fr if pinned else h_fr_pageable)[j]
+        outs, pyr = (out_np, pyr_np) if pinned else (out_pageable, pyr_pageable)
+        if order == "reference":
+            res = seg.segmentImage(left, out=outs)
+            fl_ = pool.submit(orb_l, gl, None, want_pyramid=True, pyramid_buffers=pyr[0])
+            fr_ = pool.submit(orb_r, gr, None, want_pyramid=True, pyramid_buffers=pyr[1])
+        else:
+            fl_ = pool.submit(orb_l, gl, None, want_pyramid=True, pyramid_buffers=pyr[0])
+            fr_ = pool.submit(orb_r, gr, None, want_pyramid=True, pyramid_buffers=pyr[1])
+            res = seg.segmentImage(left, out=outs)
+        out = [fl_.result(), fr_.result()]
+        if world > 1:
+            # N > 1: the frame's record is shared with every rank (SURVEY 8e) -- pack the host results, upload, all-gather, wait
+            k = i & 1
+            record.pack_host(h_rec[k], hw, kp_cap, rank * 100000 + i, res[0], res[1], res[2], out[0][0], out[0][1], out[1][0], out[1][1])
+            d_rec[k].copy_(h_rec_t[k], non_blocking=True)
+            dist.all_gather_into_tensor(d_all[k], d_rec[k])
+            torch.cuda.current_stream(dev).synchronize()
+        return res, out
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -386,6 +410,10 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- value: inputs resident in HBM
+    # set-up, not a step: the library captures one CUDA graph per (input, output, stream) pointer set the caller uses; touch every
+    # input buffer of the rotation once so that no capture falls into the timed region whatever --warmup is
+    for i in range(2 * n_frames):
+        device_step(i)
     for i in range(args.warmup):
         device_step(i)
     barrier()
@@ -396,31 +424,42 @@ def main():
     e0.record(stream)
     t0 = time.perf_counter()
     launches = 0
+    step_t = [time.perf_counter()]
     for i in range(args.steps):
         device_step(args.warmup + i)
         launches += seg.last_timing()["launches"] + orb_l.last_timing()["launches"] + orb_r.last_timing()["launches"]
+        step_t.append(time.perf_counter())
+    step_ms = 1e3 * np.diff(step_t)  # host-side issue time of each step (the last steps' GPU work drains before `elapsed` is read)
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
+    prof_value = dict(prof)  # the sustained leg and the e2e variants call device_step / the extractors again
     dev_ms = e0.elapsed_time(e1)
     elapsed = max(wall, dev_ms / 1e3)  # the ORB streams are the library's own; wall brackets everything (synced both sides)
-    # ---- e2e: host buffers through the operator calls
-    for i in range(max(2, args.warmup // 2)):
-        host_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        res, out = host_step(args.warmup + i)
-    barrier()
-    e2e_elapsed = time.perf_counter() - t0
+    # ---- e2e: host buffers through the operator calls, three call patterns (the first is the headline)
+    e2e_times = {}
+    for name, order, pinned in (("reference_order_pinned", "reference", True), ("concurrent_pinned", "concurrent", True),
+                                ("reference_order_pageable", "reference", False)):
+        for i in range(max(2, args.warmup // 2)):
+            host_step(i, order, pinned)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            res, out = host_step(args.warmup + i, order, pinned)
+        barrier()
+        e2e_times[name] = time.perf_counter() - t0
+    e2e_elapsed = e2e_times["reference_order_pinned"]
     clocks = sampler.stop() if rank == 0 else None
     n_kp = len(out[0][0]) + len(out[1][0])
     h2d = 1242 * 375 * 0 + hw * 3 + 2 * hw + n_kp * 8
     d2h = hw * 17 + n_kp * 36 + 2 * (32768 * 4 + 9 * 4) + 2 * sum((int(round(NET_H / 1.2 ** l)) + 38) * (int(round(NET_W / 1.2 ** l)) + 38 + 15) for l in range(8))
     if world > 1:
-        tt = torch.tensor([elapsed, e2e_elapsed], dtype=torch.float64, device=dev)
+        names = sorted(e2e_times)
+        tt = torch.tensor([elapsed] + [e2e_times[n] for n in names], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        elapsed, e2e_elapsed = float(tt[0]), float(tt[1])
+        elapsed = float(tt[0])
+        e2e_times = {n: float(v) for n, v in zip(names, tt[1:])}
+        e2e_elapsed = e2e_times["reference_order_pinned"]
 
     # ---- roofline of the dominant kernel: per-op CUDA events on the launching stream (profiling pass)
     roof = None
@@ -435,35 +474,75 @@ def main():
             tot_ms.append(tm["total_ms"])
             per_op.append(seg.op_timings())
         seg.set_profiling(False)
-        # dominant kernel = the launch with the most algorithmic flops (conv_decode1 + classifier in both models)
+        # dominant kernel = the launch that EXECUTES the most multiply-adds (ties: the longer one).  Executed == algorithmic
+        # except for the composed conv_decode1 x classifier layer (one 64 -> 16 convolution: 217 GF for the reference's 872) and
+        # the split-operand fp32 mode (3 MMAs per product); the roofline counts what runs, the algorithmic figure rides along
         names = [o[0] for o in per_op[0]]
-        op_flops = [o[2] for o in per_op[0]]
+        op_alg = [o[2] for o in per_op[0]]
+        op_flops = seg.op_flops_executed()
         op_ms = np.mean([[o[1] for o in run] for run in per_op], axis=0)
-        dom = int(np.argmax(op_flops))
+        dom = int(np.lexsort((op_ms, op_flops))[-1])
         fl = seg.flops()
+        fl["exec"] = float(sum(op_flops))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak = peaks.get("bf16_tflops_sustained") or 1400.0
-        which = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF sustained (B200_PROFILING.md)"
+        # the kernel is timed alone, by CUDA events, in a pass of <= 10 frames (milliseconds): burst regime -> the burst peak
+        peak = peaks.get("bf16_tflops") or 1650.0
+        which = "measured burst (MEASURED_PEAKS.json bf16_tflops): kernel timed alone in a <=10-frame pass" if peaks.get("bf16_tflops") \
+            else "fallback 1.65 PF burst (B200_PROFILING.md)"
+        peak_sus = peaks.get("bf16_tflops_sustained") or 1400.0
         ach = op_flops[dom] / (op_ms[dom] * 1e-3) / 1e12
-        ach_all = fl["dedup"] / (np.mean(conv_ms) * 1e-3) / 1e12
+        ach_all = fl["exec"] / (np.mean(conv_ms) * 1e-3) / 1e12
         traffic = None
-        try:  # dram bytes of that kernel from the committed `ncu --set full` capture (tools/ncu_summary.py writes it)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            traffic = tj.get(args.model, {}).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+        for tf in ("r2_traffic.json", "r1_traffic.json"):  # dram bytes of that kernel from the committed `ncu --set full` capture
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", tf)))
+                traffic = tj.get(args.model, {}).get("dram_bytes_per_launch")
+                if traffic:
+                    break
+            except Exception:
+                pass
+        # ---- sustained leg: >= --sustain-seconds of back-to-back work with its own clock samples, against the SUSTAINED peak
+        sustained = None
+        if args.sustain_seconds > 0 and world == 1:
+            sustained = {}
+            for leg in ("segnet_only", "full_step"):
+                sm = ClockSampler(local_rank)
+                sm.start()
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                n_done = 0
+                while time.perf_counter() - t0 < args.sustain_seconds:
+                    for _ in range(50):
+                        if leg == "segnet_only":
+                            seg.run_device(d_bgr[n_done % n_frames].data_ptr(), d_cls.data_ptr(), d_conf.data_ptr(), d_ent.data_ptr(), stream.cuda_stream)
+                        else:
+                            device_step(n_done)
+                        n_done += 1
+                    if leg == "segnet_only":
+                        torch.cuda.synchronize(dev)  # bounded queue depth; the GPU is re-fed within microseconds
+                torch.cuda.synchronize(dev)
+                dt = time.perf_counter() - t0
+                tf_s = fl["exec"] * n_done / dt / 1e12
+                sustained[leg] = {"seconds": round(dt, 3), "frames": n_done, "frames_per_s": n_done / dt, "ms_per_frame": 1e3 * dt / n_done,
+                                  "conv_tflops_executed": tf_s, "frac_of_sustained_peak": tf_s / peak_sus,
+                                  "conv_tflops_algorithmic": fl["dedup"] * n_done / dt / 1e12, "clocks": sm.stop()}
+            sustained["peak"] = peak_sus
+            sustained["peak_source"] = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks.get("bf16_tflops_sustained") else "fallback 1.4 PF"
+            sustained["note"] = "conv_tflops_executed = executed conv FLOPs per frame x frames / wall seconds of the whole leg (non-conv kernels and, in full_step, the extractors included)"
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "kernel": f"tcgen05 convolution launch '{names[dom]}'", "peak_source": which,
-                "kernel_ms": float(op_ms[dom]), "kernel_gflop": op_flops[dom] / 1e9,
+                "kernel_ms": float(op_ms[dom]), "kernel_gflop": op_flops[dom] / 1e9, "kernel_gflop_algorithmic": op_alg[dom] / 1e9,
+                "flops_counted": "executed multiply-adds x 2 (see kernel_gflop_algorithmic / algorithmic_gflop_per_frame for the reference's operation count)",
                 "all_conv_launches": {"achieved": ach_all, "frac": ach_all / peak, "ms_per_frame": float(np.mean(conv_ms)),
-                                      "gflop_per_frame": fl["dedup"] / 1e9},
+                                      "gflop_per_frame": fl["exec"] / 1e9, "algorithmic_tflops": fl["dedup"] / (np.mean(conv_ms) * 1e-3) / 1e12},
                 "conv_ms_per_frame": float(np.mean(conv_ms)), "segnet_ms_per_frame": float(np.mean(tot_ms)),
-                "algorithmic_gflop_per_frame": fl["dedup"] / 1e9, "naive_gflop_per_frame": fl["naive"] / 1e9,
-                "launch_ms": {n: round(float(m), 4) for n, m in zip(names, op_ms)}}
+                "algorithmic_gflop_per_frame": fl["dedup"] / 1e9, "executed_gflop_per_frame": fl["exec"] / 1e9, "naive_gflop_per_frame": fl["naive"] / 1e9,
+                "launch_ms": {n: round(float(m), 4) for n, m in zip(names, op_ms)},
+                "launch_gflop": {n: round(f / 1e9, 2) for n, f in zip(names, op_flops)}, "sustained": sustained}
         if not args.no_cpu_baseline and world == 1:
             if all_cpus:  # the baseline gets every host core again (all threads of the process, incl. any OpenMP workers)
                 try:
@@ -484,10 +563,12 @@ def main():
                 "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "f32", "data": "synthetic",
                 "config": workload_config(args, T), "clocks": clocks,
                 "e2e": {"value": total_frames / e2e_elapsed, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h)},
+                        "d2h_bytes_per_step": int(d2h), "calls": "reference order (segmentImage, then the two extractor threads), page-locked buffers"},
+                "e2e_variants": {n: {"value": total_frames / t, "unit": "frames/s", "ms_per_step": 1e3 * t / args.steps} for n, t in e2e_times.items()},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu_base,
-                "host_ms_per_step": {k: round(1e3 * v / (args.steps + args.warmup), 3) for k, v in prof.items()},
+                "host_ms_per_step": {k: round(1e3 * v / (args.steps + args.warmup + 2 * n_frames), 3) for k, v in prof_value.items()},
                 "orb_last_call": {"left": orb_l.last_timing(), "right": orb_r.last_timing()},
+                "host_issue_ms_per_step": {"min": float(step_ms.min()), "median": float(np.median(step_ms)), "max": float(step_ms.max())},
                 "keypoints_last_frame": int(n_kp)}
         print(json.dumps(line))
     if world > 1:

@@ -104,6 +104,10 @@ int sivo_segnet_flops(const sivo_segnet_t* h, double* conv_flops_dedup, double* 
  * (ms, CUDA events on the launching stream) and its algorithmic convolution flops (0 for non-convolution launches). */
 int sivo_segnet_op_timing(const sivo_segnet_t* h, int index, char* name, size_t cap, float* ms, double* flops,
                           int* n_ops);
+/* Multiply-add work a launch EXECUTES on the tensor / CUDA cores, as flops (2 x MACs).  Equals the algorithmic figure of
+ * sivo_segnet_op_timing except where the library changes the operation count: the composed conv_decode1 x classifier layer
+ * (one 64 -> 16 7x7 convolution instead of 64 -> 64 followed by 64 -> 15: 0.25x) and the split-operand fp32 mode (3x). */
+int sivo_segnet_op_flops_executed(const sivo_segnet_t* h, int index, double* flops);
 void sivo_segnet_destroy(sivo_segnet_t* h);
 
 /* ---- ORB extractor ---------------------------------------------------------------------------- */

@@ -129,6 +129,16 @@ int sivo_segnet_op_timing(const sivo_segnet_t* h, int index, char* name, size_t 
   });
 }
 
+int sivo_segnet_op_flops_executed(const sivo_segnet_t* h, int index, double* flops) {
+  return guarded([&] {
+    if (!h) fail(SIVO_EINVAL, "null handle");
+    const int n = static_cast<int>(h->impl->n_ops());
+    if (index < 0 || index >= n) fail(SIVO_ERANGE, "op index %d out of range (%d launches)", index, n);
+    const Op& op = h->impl->op_at(index);
+    if (flops) *flops = op.kind == Op::Conv ? op.flops_exec : 0.0;
+  });
+}
+
 int sivo_segnet_flops(const sivo_segnet_t* h, double* dedup, double* naive) {
   return guarded([&] {
     if (!h) fail(SIVO_EINVAL, "null handle");

@@ -59,6 +59,8 @@ struct TcParams {
                            // [W_hi | W_lo | W_hi]; `chunks` then counts A chunks (2 * Cin / 64: hi and lo of each, interleaved)
   int cin_real;            // Cin (split mode: channel offset of the lo plane)
   float acc_scale;         // split mode: the weights were scaled by a power of two before the hi/lo split; 1 / that
+  float rz_comp;           // split mode: expected truncation loss per accumulate step relative to the running sum (see seg_rows);
+                           // each flushed segment of m steps is scaled by 1 + rz_comp * m before it is added (0 = off)
   int seg_rows;            // split mode: tap rows per accumulation segment.  The tensor core adds into its fp32 accumulator with
                            // truncation (measured: ~2^-25 relative per accumulate step, always towards zero, so it grows linearly
                            // with the chain length: 1.4e-5 for a 7x7x64 layer); the block's MMAs are therefore cut into segments
@@ -630,8 +632,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         float accr[128];
 #pragma unroll
         for (int i = 0; i < 128; ++i) accr[i] = 0.f;
+        const int segs_per_chunk = (K + p.seg_rows - 1) / p.seg_rows;
         for (int sg = 0; sg < segs; ++sg, ++seg) {
           const int acc = seg & 1;
+          // accumulate steps of this segment: (tap rows) x KW x 4 K steps x (2 weight tiles for a hi chunk, 1 for a lo chunk).
+          // The tensor core truncates each add towards zero: mean loss 0.36 x 2^-23 of the running sum per step (half an ulp,
+          // ulp / |x| averaging 0.72 x 2^-23 over a binade), and a sum growing from 0 averages ~0.6 of its final value, so the
+          // segment comes back short by ~0.216 x 2^-23 x m of itself: scaled back up here (leaves the zero-mean part).
+          const int ch_s = sg / segs_per_chunk, kh0 = (sg % segs_per_chunk) * p.seg_rows;
+          const int m_steps = min(p.seg_rows, K - kh0) * KW * 4 * ((ch_s & 1) ? 1 : 2);
+          const float comp = 1.f + p.rz_comp * static_cast<float>(m_steps);
           mbar_wait(t_full + acc, (seg >> 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + y_row) * p.n_tile);
@@ -639,7 +649,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             uint32_t v[32];
             tmem_ld16(trow, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) accr[i] = __fadd_rn(accr[i], __uint_as_float(v[i]));
+            for (int i = 0; i < 16; ++i) accr[i] = __fmaf_rn(__uint_as_float(v[i]), comp, accr[i]);
           } else {
 #pragma unroll
             for (int cc = 0; cc < 128; cc += 32)
@@ -647,7 +657,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 uint32_t v[32];
                 tmem_ld32(trow + cc, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) accr[cc + i] = __fadd_rn(accr[cc + i], __uint_as_float(v[i]));
+                for (int i = 0; i < 32; ++i) accr[cc + i] = __fmaf_rn(__uint_as_float(v[i]), comp, accr[cc + i]);
               }
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -966,6 +976,166 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Full-stack variant for the composed 64 -> 16 layer (Basic: conv_decode1 x the 1x1 classifier as ONE 7x7 convolution with
+// 16 output columns, see conv_tc_set_composed_classifier).  With N = 16 per tap an MMA is bound by its 4 KB A read, so ALL
+// seven tap rows are stacked along N: input row i of a block feeds acc(r) for every output row r with 0 <= i - r <= 6, one
+// MMA of N = 16 x (number of such rows) <= 112 per (input row, kw, K step).  Accumulators sit in decreasing row order and
+// the weights in increasing tap order, so each MMA covers one contiguous TMEM column range and one contiguous weight range.
+//  * R = 16 output rows per block, 2 accumulator stages x 16 rows x 16 columns = all 512 TMEM columns.
+//  * The composed weights (49 taps x 16 x 64 half = 98 KB) stay resident in shared memory: no weight ring.
+//  * Every input row is consumed by 28 consecutive MMAs and then dead: the halo ring is pure prefetch depth (7 slots).
+//  * Model: per (kw, K step) a block issues MMAs of N = 16, 32, .., 96, 112 x 10, 96, .., 16 for its 22 input rows =
+//    1152 cycles (N = 112: 56 tensor cycles against 60 of shared-memory operand reads) -> 32 K cycles per 16 x 128 px.
+constexpr int kStackRows = 16, kStackSlots = 7;
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_conv_tc_stack16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcParams p,
+                  const __grid_constant__ TcConsts cst) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  constexpr int K = 7, R = kStackRows, kSlots = kStackSlots, kPad = 3, NW = 16;
+  constexpr int kTapBytes = NW * 128, kKwBytes = K * kTapBytes, kWBytes = K * kKwBytes;  // 2 KB, 14 KB, 98 KB
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* w_smem = smem;                         // [kw][kh][16][64] half, K-major SWIZZLE_128B rows
+  uint8_t* a_slots = smem + kWBytes;              // kWBytes is a multiple of 1024
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_slots + kSlots * kSlotBytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kSlots;
+  uint64_t* w_full = a_empty + kSlots;
+  uint64_t* t_full = w_full + 1;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int strip = blockIdx.x % p.strips, rowblk = blockIdx.x / p.strips;
+  const int img = blockIdx.z;
+  const int x0 = strip * 128;
+  const int total_blocks = (p.H + R - 1) / R;
+  const int blk0 = rowblk * p.pairs_per_cta;
+  const int nblk = min(p.pairs_per_cta, total_blocks - blk0);
+  constexpr uint32_t tmem_cols = 2 * R * NW;  // 512
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSlots; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+  if (warp == 0) {
+    // ===== halo-row producer: R + 6 input rows per block, in order, through the ring =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+      uint32_t u = 0;
+      for (int j = 0; j < nblk; ++j) {
+        const int y0 = (blk0 + j) * R;
+        for (int i = 0; i < R + K - 1; ++i, ++u) {
+          const int slot = u % kSlots;
+          mbar_wait(a_empty + slot, ((u / kSlots) & 1) ^ 1);
+          mbar_expect_tx(a_full + slot, static_cast<uint32_t>((128 + K - 1) * 128));
+          tma_load_4d(a_slots + slot * kSlotBytes, &map_a, a_full + slot, 0, x0 - kPad, y0 - kPad + i, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== weights: loaded once, resident =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+      mbar_expect_tx(w_full, static_cast<uint32_t>(kWBytes));
+      for (int kw = 0; kw < K; ++kw)  // one box {64 cin, 7 taps x 16 rows} per tap column
+        tma_load_3d(w_smem + kw * kKwBytes, &map_b, w_full, 0, kw * K * NW, 0);
+    }
+  } else if (warp == 2) {
+    // ===== MMA issuer =====
+    const uint32_t a_base = smem_u32(a_slots), w_base = smem_u32(w_smem);
+    const uint64_t hi = static_cast<uint64_t>(kDescHi) << 32;
+    mbar_wait(w_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t u = 0;
+    for (int j = 0; j < nblk; ++j) {
+      const int acc = j & 1;
+      mbar_wait(t_empty + acc, ((j >> 1) & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d0 = tmem_base + static_cast<uint32_t>(acc * R * NW);  // acc(r) sits at d0 + (R - 1 - r) * NW
+      for (int i = 0; i < R + K - 1; ++i, ++u) {
+        const int slot = u % kSlots;
+        mbar_wait(a_full + slot, (u / kSlots) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int r_hi = min(R - 1, i), r_lo = max(0, i - (K - 1));
+        const int cnt = r_hi - r_lo + 1;             // output rows this input row feeds
+        const int kh_lo = i - r_hi;                  // tap row meeting acc(r_hi); acc(r_hi - t) meets tap kh_lo + t
+        const uint32_t d = d0 + static_cast<uint32_t>((R - 1 - r_hi) * NW);
+        const uint32_t a_lo = (((a_base + slot * kSlotBytes) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t b_lo = (((w_base + kh_lo * kTapBytes) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>((cnt * NW) >> 3) << 17) | (8u << 24);
+        if (elect_one()) {
+          if (i < R) {
+            // acc(i) meets its first tap here (kh = 0, kw = 0, K step 0): that MMA must clear it, the rest of the stack accumulates
+            const uint32_t idesc1 = (1u << 4) | (static_cast<uint32_t>(NW >> 3) << 17) | (8u << 24);
+            umma_f16(d, hi | a_lo, hi | b_lo, idesc1, 0u);
+            if (cnt > 1) {
+              const uint32_t idesc_r = (1u << 4) | (static_cast<uint32_t>(((cnt - 1) * NW) >> 3) << 17) | (8u << 24);
+              umma_f16(d + NW, hi | a_lo, hi | (b_lo + (kTapBytes >> 4)), idesc_r, 1u);
+            }
+#pragma unroll
+            for (int k = 1; k < 4; ++k) umma_f16(d, hi | (a_lo + 2 * k), hi | (b_lo + 2 * k), idesc, 1u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(d, hi | (a_lo + 2 * k), hi | (b_lo + 2 * k), idesc, 1u);
+          }
+#pragma unroll
+          for (int kw = 1; kw < K; ++kw)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(d, hi | (a_lo + 8 * kw + 2 * k), hi | (b_lo + kw * (kKwBytes >> 4) + 2 * k), idesc, 1u);
+          umma_commit(a_empty + slot);   // the row is dead once these MMAs retire
+          if (i == R + K - 2) umma_commit(t_full + acc);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
+    // ===== epilogue: 16 float logits per pixel straight from the accumulators (+ composed bias), 4-lane transposed stores =====
+    const int q = warp & 3;
+    const int eset = (warp - 4) >> 2;  // two warps per TMEM lane quarter: rows [0, 8) and [8, 16) of the block
+    const int x = x0 + q * 32 + lane;
+    for (int j = 0; j < nblk; ++j) {
+      const int acc = j & 1;
+      mbar_wait(t_full + acc, (j >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 2
+      for (int rr = 0; rr < R / 2; ++rr) {
+        const int r = eset * (R / 2) + rr;
+        const int y = (blk0 + j) * R + r;
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * R * NW + (R - 1 - r) * NW);
+        epilogue_row(p, cst, trow, img, y, x, 0, lane);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + acc);
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
 // ---- host: tensor maps through the driver entry point (no -lcuda at link time)
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1004,7 +1174,8 @@ struct ConvTcPlan {
   bool roll;
   bool pair = false;  // paired-tap kernel (64 -> 64 channels, 4-row blocks)
   bool triple = false;  // ... with taps 4..6 stacked three-high (K = 7)
-  bool nw16 = false;    // ... with 16-wide accumulators: conv composed with the 1x1 classifier (experimental)
+  bool nw16 = false;    // ... with 16-wide accumulators: conv composed with the 1x1 classifier
+  bool stack16 = false; // composed 64 -> 16 layer on the full-stack kernel (all seven tap rows stacked along N, resident weights)
   DevBuf w_replicas;  // private replicated copy of the weights (w_rep > 1)
 };
 
@@ -1036,7 +1207,8 @@ void conv_tc_dispatch(const ConvTcPlan& plan, cudaStream_t s, bool configure) {
     }
   };
   const int K = plan.k;
-  if (plan.pair && plan.nw16) go(k_conv_tc_pair<7, true, 16>);
+  if (plan.stack16) go(k_conv_tc_stack16);
+  else if (plan.pair && plan.nw16) go(k_conv_tc_pair<7, true, 16>);
   else if (plan.pair) { if (K == 7 && plan.triple) go(k_conv_tc_pair<7, true>); else if (K == 7) go(k_conv_tc_pair<7>); else go(k_conv_tc_pair<3>); }
   else if (plan.kw == 1 && K > 1) {  // window-folded first layer (K x 1)
     if (!plan.roll) fail(SIVO_EINVAL, "window-folded convolution needs the rolling kernel");
@@ -1152,8 +1324,10 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   p.split = op.split ? 1 : 0;
   p.cin_real = op.cin;
   p.acc_scale = op.split ? op.acc_scale : 1.f;
-  p.seg_rows = K == 7 ? 1 : K;  // 7x7: a segment per (chunk, tap row) = 56 / 28 accumulate steps; 3x3 / 1x1: per chunk (72 / 36, 8 / 4)
+  p.seg_rows = 1;  // a segment per (chunk, tap row): 7x7 56 / 28 accumulate steps, 3x3 24 / 12, 1x1 8 / 4 (measured: profiles/r2_parity.md)
   if (const char* e = std::getenv("SIVO_B200_SPLIT_SEG")) p.seg_rows = std::max(1, std::min(K, atoi(e)));
+  p.rz_comp = 0.216f * 1.1920929e-7f;  // x 2^-23
+  if (const char* e = std::getenv("SIVO_B200_SPLIT_RZ")) p.rz_comp = static_cast<float>(atof(e)) * 1.1920929e-7f;
   p.strips = ceil_div(p.W, 128);
   const int cout_tiles = p.out_f32 == 1 ? 1 : op.cout_p / n_tile;
   const int columns = p.strips * in.n * cout_tiles;
@@ -1337,9 +1511,29 @@ void conv_tc_set_composed_classifier(ConvTcPlan& plan, const Op& conv, const flo
   p.cout_total = 16;
   p.out = logits;
   p.w_rep = 1;
-  p.b_stages = 6;
-  plan.nw16 = true;
-  plan.smem = 1024 + static_cast<size_t>(9) * kSlotBytes + static_cast<size_t>(p.b_stages) * 3 * 16 * 128 + (2 * 9 + 2 * p.b_stages + 4) * 8 + 16;
+  const char* stack_env = std::getenv("SIVO_B200_STACK16");
+  if (!(stack_env && stack_env[0] == '0')) {
+    // full-stack kernel: one weight box per tap column {64 cin, 7 taps x 16 rows}, 16-row blocks
+    cuuint32_t box_s[3] = {64, 7 * 16, 1};
+    encode(&plan.map_b, plan.w_replicas.p, 3, dims, strides, box_s);
+    plan.stack16 = true;
+    const int total_blocks = ceil_div(p.H, kStackRows);
+    const int columns = p.strips * p.N_batch;
+    int ppc = 1;
+    double best_cost = 1e30;
+    for (int c = 1; c <= std::min(total_blocks, 24); ++c) {  // (waves of 148 SMs) x (blocks per CTA + weight load / prologue)
+      const long ctas = static_cast<long>(columns) * ceil_div(total_blocks, c);
+      const double cost = static_cast<double>((ctas + 147) / 148) * (c + 0.35);
+      if (cost < best_cost - 1e-9) { best_cost = cost; ppc = c; }
+    }
+    p.pairs_per_cta = ppc;
+    plan.grid = dim3(p.strips * ceil_div(total_blocks, ppc), 1, p.N_batch);
+    plan.smem = 1024 + static_cast<size_t>(7) * 7 * 16 * 128 + static_cast<size_t>(kStackSlots) * kSlotBytes + (2 * kStackSlots + 1 + 4) * 8 + 16;
+  } else {
+    p.b_stages = 6;
+    plan.nw16 = true;
+    plan.smem = 1024 + static_cast<size_t>(9) * kSlotBytes + static_cast<size_t>(p.b_stages) * 3 * 16 * 128 + (2 * 9 + 2 * p.b_stages + 4) * 8 + 16;
+  }
   conv_tc_dispatch(plan, nullptr, true);
 }
 

@@ -236,21 +236,31 @@ void SegNet::build(const NetSpec& net, const WeightMap& weights) {
         }
         prepare_conv(op, it->second, bn);
         op.flops = 2.0 * iv.c * ly.kernel * ly.kernel * op.cout * iv.h * iv.w * iv.n;  // algorithmic, whatever the mapping
+        op.flops_exec = op.split ? 3.0 * op.flops : op.flops;
         flops_dedup += op.flops;
         flops_naive += op.flops / iv.n * T_;
         if (logits && !opt_.keep_blobs && op.k == 1 && op.cin == 64 && op.cout <= 16 && !op.relu && !bn && !ops_.empty() &&
             ops_.back().kind == Op::Conv && ops_.back().use_tc && ops_.back().out == in && conv_tc_can_fuse_classifier(*ops_.back().tc)) {
           // 1x1 classifier straight after a tensor-core convolution: computed in that convolution's epilogue from the
           // half-rounded activations, so the 64-channel tensor is never written or re-read
+          // No non-linearity sits between the two layers (Basic), so logits = (Wc W) * x + (Wc b + bc): ONE 64 -> 16 convolution
+          // with weights composed in double and rounded to half once -- a quarter of the multiply-adds, and closer to the
+          // reference's fp32 arithmetic than the two-step half path (the 64-channel activation is never rounded to half;
+          // tests/test_gpu_parity.py, tools/compose_classifier_study.py).  Default; SIVO_B200_COMPOSE=0 keeps the two-step form.
           const char* compose = std::getenv("SIVO_B200_COMPOSE");
-          if (compose && compose[0] == '1' && !ops_.back().relu && !ops_.back().has_bn && conv_tc_can_compose_classifier(*ops_.back().tc))
-            conv_tc_set_composed_classifier(*ops_.back().tc, ops_.back(), op.h_w_raw.data(), op.h_bias.data(), op.cout,
+          Op& conv = ops_.back();
+          if (!(compose && compose[0] == '0') && !conv.relu && !conv.has_bn && conv_tc_can_compose_classifier(*conv.tc)) {
+            conv_tc_set_composed_classifier(*conv.tc, conv, op.h_w_raw.data(), op.h_bias.data(), op.cout,
                                             static_cast<float*>(tensors_[op.out]->v.p));
-          else
-            conv_tc_set_classifier(*ops_.back().tc, op.h_w.data(), op.cout_p, op.h_bias.data(), std::min(16, op.cout_p),
+            conv.flops_exec = 2.0 * conv.cin * conv.k * conv.k * 16 * iv.h * iv.w * iv.n;  // the 16-wide composed layer
+            conv.layer += "*" + ly.name;  // '*': composed, not merely fused
+          } else {
+            conv_tc_set_classifier(*conv.tc, op.h_w.data(), op.cout_p, op.h_bias.data(), std::min(16, op.cout_p),
                                    static_cast<float*>(tensors_[op.out]->v.p));
-          ops_.back().layer += "+" + ly.name;
-          ops_.back().flops += op.flops;  // the classifier's multiply-adds run inside that launch
+            conv.flops_exec += op.flops;
+            conv.layer += "+" + ly.name;
+          }
+          conv.flops += op.flops;  // algorithmic: the reference runs both layers
           tensors_[in]->elided = true;
           fused_.push_back(std::move(op));
           li = lj - 1;

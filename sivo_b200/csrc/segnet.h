@@ -49,7 +49,8 @@ struct Op {
   DevBuf a_split;
   std::shared_ptr<ConvTcPlan> tc;
   bool use_tc = false;
-  double flops = 0;  // algorithmic, for this op's batch
+  double flops = 0;       // algorithmic (the reference's operation count), for this op's batch
+  double flops_exec = 0;  // what the launch executes: differs for the composed classifier (0.25x) and the split-operand mode (3x)
   // Dropout
   int drop_layer = 0;
   float drop_scale = 2.f;

@@ -37,6 +37,15 @@ def pack_host_part(buf: np.ndarray, hw: int, kp_cap: int, frame_id: int, kl, dl,
     buf[o["desc_right"]:o["desc_right"] + nr * 32] = np.ascontiguousarray(dr, np.uint8).reshape(-1)
 
 
+def pack_host(buf: np.ndarray, hw: int, kp_cap: int, frame_id: int, classes, conf, ent, kl, dl, kr, dr) -> None:
+    """The whole record from host results (the e2e path, where segmentImage has already copied the maps to the host)."""
+    o = offsets(hw, kp_cap)
+    buf[o["classes"]:o["classes"] + hw] = classes.reshape(-1)
+    buf[o["confidence"]:o["confidence"] + hw * 8] = conf.reshape(-1).view(np.uint8)
+    buf[o["entropy"]:o["entropy"] + hw * 8] = ent.reshape(-1).view(np.uint8)
+    pack_host_part(buf, hw, kp_cap, frame_id, kl, dl, kr, dr)
+
+
 def unpack(buf: np.ndarray, h: int, w: int, kp_cap: int):
     hw = h * w
     o = offsets(hw, kp_cap)

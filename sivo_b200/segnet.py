@@ -115,6 +115,17 @@ class BayesianSegNet:
                                          None, None, None, None))
         return out
 
+    def op_flops_executed(self):
+        """Executed conv flops per launch (== algorithmic except for the composed classifier and the split-operand mode)."""
+        n = C.c_int()
+        L.check(L.lib().sivo_segnet_op_timing(self._h, -1, None, 0, None, None, C.byref(n)))
+        out = []
+        for i in range(n.value):
+            fl = C.c_double()
+            L.check(L.lib().sivo_segnet_op_flops_executed(self._h, i, C.byref(fl)))
+            out.append(fl.value)
+        return out
+
     def op_timings(self):
         """[(layer names, ms in the last profiled run, algorithmic conv flops)] per launch of the op list."""
         n = C.c_int()
