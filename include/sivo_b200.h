@@ -128,6 +128,16 @@ int sivo_orb_run(sivo_orb_t* h, const uint8_t* gray, int rows, int cols, size_t 
  * candidate / selection round trip through the host quad tree stays inside the call. */
 int sivo_orb_run_device_input(sivo_orb_t* h, const uint8_t* gray_device, int rows, int cols, size_t pitch,
                               sivo_keypoint* kps, int cap, int* n, uint8_t* desc32);
+/* Fully asynchronous operator for device-resident pipelines (frame sharding across GPUs, CUDA-graph style callers): enqueues
+ * pyramid -> FAST -> cells -> device quad tree -> blur -> rBRIEF on the handle's own stream and returns without synchronising.
+ * kps_device needs room for sivo_orb_capacity(h) records, desc32_device for 32 bytes each; *count_device (int64) receives the
+ * keypoint count.  sivo_orb_stream_wait makes another stream wait for the enqueued work; sivo_orb_device_status (synchronises)
+ * returns a non-zero level mask if a level exceeded the device tree's capacity (use sivo_orb_run for such inputs). */
+int sivo_orb_enqueue_device(sivo_orb_t* h, const uint8_t* gray_device, int rows, int cols, size_t pitch, sivo_keypoint* kps_device,
+                            uint8_t* desc32_device, long long* count_device);
+int sivo_orb_stream_wait(sivo_orb_t* h, void* consumer_cuda_stream);
+int sivo_orb_device_status(sivo_orb_t* h, int* level_mask);
+int sivo_orb_capacity(const sivo_orb_t* h, int* max_keypoints);
 int sivo_orb_level_size(const sivo_orb_t* h, int rows, int cols, int level, int* level_w, int* level_h);
 /* Test hook: FAST candidates of the last run before the quad tree, per level (x, y relative to the
  * (16,16) border origin as in ComputeKeyPointsOctTree, response). */
@@ -139,6 +149,12 @@ void sivo_orb_destroy(sivo_orb_t* h);
  * tests share one implementation of the documented tie rule.  Returns the number of kept indices. */
 int sivo_orb_distribute(const float* xs, const float* ys, const float* resp, int n, int min_x, int max_x,
                         int min_y, int max_y, int n_target, int* keep, int cap);
+
+/* Test hook: the same distribution on the DEVICE quad tree (orb_tree.cu), integer key coordinates < 4096 and responses < 256
+ * as the FAST stage produces them.  Writes the kept keys' (x, y, response) in list order; returns their count, or
+ * SIVO_ERANGE if the input exceeds the device tree's capacity. */
+int sivo_dbg_orb_distribute_device(int device, const int* xs, const int* ys, const int* resp, int n, int min_x, int max_x,
+                                   int min_y, int max_y, int n_target, int* out_x, int* out_y, int* out_resp, int cap);
 
 /* ---- stereo Hamming stage (next-row 1) -------------------------------------------------------- */
 /* For each left keypoint: best right candidate in its row band (rows vL +- 2*scale[octave]), octave

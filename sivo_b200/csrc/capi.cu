@@ -2,6 +2,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <string>
 
@@ -193,6 +194,36 @@ int sivo_orb_run_device_input(sivo_orb_t* h, const uint8_t* gray_device, int row
   });
 }
 
+int sivo_orb_enqueue_device(sivo_orb_t* h, const uint8_t* gray_device, int rows, int cols, size_t pitch, sivo_keypoint* kps_device,
+                            uint8_t* desc32_device, long long* count_device) {
+  return guarded([&] {
+    if (!h) fail(SIVO_EINVAL, "null handle");
+    h->impl->enqueue_device(gray_device, rows, cols, pitch, kps_device, desc32_device, count_device);
+  });
+}
+
+int sivo_orb_stream_wait(sivo_orb_t* h, void* consumer_cuda_stream) {
+  return guarded([&] {
+    if (!h) fail(SIVO_EINVAL, "null handle");
+    h->impl->stream_wait(static_cast<cudaStream_t>(consumer_cuda_stream));
+  });
+}
+
+int sivo_orb_device_status(sivo_orb_t* h, int* level_mask) {
+  return guarded([&] {
+    if (!h) fail(SIVO_EINVAL, "null handle");
+    const int m = h->impl->device_tree_status();
+    if (level_mask) *level_mask = m;
+  });
+}
+
+int sivo_orb_capacity(const sivo_orb_t* h, int* max_keypoints) {
+  return guarded([&] {
+    if (!h) fail(SIVO_EINVAL, "null handle");
+    if (max_keypoints) *max_keypoints = h->impl->capacity();
+  });
+}
+
 int sivo_orb_level_size(const sivo_orb_t* h, int rows, int cols, int level, int* level_w, int* level_h) {
   return guarded([&] {
     if (!h) fail(SIVO_EINVAL, "null handle");
@@ -232,6 +263,47 @@ int sivo_orb_distribute(const float* xs, const float* ys, const float* resp, int
     if (static_cast<int>(k.size()) > cap) fail(SIVO_ERANGE, "%zu kept keypoints, buffer holds %d", k.size(), cap);
     if (keep) memcpy(keep, k.data(), k.size() * sizeof(int));
     count = static_cast<int>(k.size());
+  });
+  return rc == SIVO_OK ? count : rc;
+}
+
+int sivo_dbg_orb_distribute_device(int device, const int* xs, const int* ys, const int* resp, int n, int min_x, int max_x, int min_y,
+                                   int max_y, int n_target, int* out_x, int* out_y, int* out_resp, int cap) {
+  int count = 0;
+  int rc = guarded([&] {
+    if (n > 0 && (!xs || !ys || !resp)) fail(SIVO_EINVAL, "null keypoint arrays");
+    if (max_x <= min_x || max_y <= min_y) fail(SIVO_EINVAL, "empty distribution rectangle");
+    SIVO_CUDA(cudaSetDevice(device));
+    orb_tree_configure();
+    OrbTreeParams prm{};
+    int n_ini = static_cast<int>(std::round(static_cast<float>(max_x - min_x) / (max_y - min_y)));
+    if (n_ini < 1) n_ini = 1;
+    prm.n_target[0] = n_target; prm.n_ini[0] = n_ini; prm.height[0] = max_y - min_y;
+    prm.hx[0] = static_cast<float>(max_x - min_x) / n_ini;
+    prm.scale[0] = 1.f; prm.size[0] = 31.f; prm.min_b = 0;
+    std::vector<uint32_t> packed(std::max(n, 1));
+    for (int i = 0; i < n; ++i) {
+      if (xs[i] < 0 || xs[i] > 4095 || ys[i] < 0 || ys[i] > 4095 || resp[i] < 0 || resp[i] > 255) fail(SIVO_EINVAL, "key %d out of range", i);
+      packed[i] = static_cast<uint32_t>(xs[i]) | (static_cast<uint32_t>(ys[i]) << 12) | (static_cast<uint32_t>(resp[i]) << 24);
+    }
+    const int off[2] = {0, n};
+    DevBuf d_cand(packed.size() * 4), d_off(sizeof off), d_sel(static_cast<size_t>(kTreeSelCap) * 4), d_cnt(2 * sizeof(int));
+    SIVO_CUDA(cudaMemcpy(d_cand.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+    SIVO_CUDA(cudaMemcpy(d_off.p, off, sizeof off, cudaMemcpyHostToDevice));
+    SIVO_CUDA(cudaMemset(d_cnt.p, 0, 2 * sizeof(int)));
+    orb_launch_distribute(d_cand.as<uint32_t>(), d_off.as<int>(), prm, 1, d_sel.as<uint32_t>(), d_cnt.as<int>(), d_cnt.as<int>() + 1, nullptr);
+    int ce[2] = {0, 0};
+    SIVO_CUDA(cudaMemcpy(ce, d_cnt.p, sizeof ce, cudaMemcpyDeviceToHost));
+    if (ce[1]) fail(SIVO_ERANGE, "input exceeds the device quad tree's capacity");
+    if (ce[0] > cap) fail(SIVO_ERANGE, "%d kept keypoints, buffer holds %d", ce[0], cap);
+    std::vector<uint32_t> sel(std::max(ce[0], 1));
+    SIVO_CUDA(cudaMemcpy(sel.data(), d_sel.p, static_cast<size_t>(ce[0]) * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < ce[0]; ++i) {
+      if (out_x) out_x[i] = static_cast<int>(sel[i] & 0xFFF);
+      if (out_y) out_y[i] = static_cast<int>((sel[i] >> 12) & 0xFFF);
+      if (out_resp) out_resp[i] = static_cast<int>(sel[i] >> 24);
+    }
+    count = ce[0];
   });
   return rc == SIVO_OK ? count : rc;
 }

@@ -987,17 +987,19 @@ k_conv_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 //  * Every input row is consumed by 28 consecutive MMAs and then dead: the halo ring is pure prefetch depth (7 slots).
 //  * Model: per (kw, K step) a block issues MMAs of N = 16, 32, .., 96, 112 x 10, 96, .., 16 for its 22 input rows =
 //    1152 cycles (N = 112: 56 tensor cycles against 60 of shared-memory operand reads) -> 32 K cycles per 16 x 128 px.
+// K = 3: the same for a 3x3 layer with <= 16 float outputs (Standard's conv1_1_D): N = 16, 32, 48 x 14, 32, 16 per (kw, K step).
 constexpr int kStackRows = 16, kStackSlots = 7;
+template <int K>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_conv_tc_stack16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcParams p,
                   const __grid_constant__ TcConsts cst) {
   asm volatile("griddepcontrol.launch_dependents;");
-  constexpr int K = 7, R = kStackRows, kSlots = kStackSlots, kPad = 3, NW = 16;
+  constexpr int R = kStackRows, kSlots = kStackSlots, kPad = (K - 1) / 2, NW = 16;
   constexpr int kTapBytes = NW * 128, kKwBytes = K * kTapBytes, kWBytes = K * kKwBytes;  // 2 KB, 14 KB, 98 KB
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* w_smem = smem;                         // [kw][kh][16][64] half, K-major SWIZZLE_128B rows
-  uint8_t* a_slots = smem + kWBytes;              // kWBytes is a multiple of 1024
+  uint8_t* a_slots = smem + ((kWBytes + 1023) & ~1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(a_slots + kSlots * kSlotBytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kSlots;
@@ -1207,7 +1209,7 @@ void conv_tc_dispatch(const ConvTcPlan& plan, cudaStream_t s, bool configure) {
     }
   };
   const int K = plan.k;
-  if (plan.stack16) go(k_conv_tc_stack16);
+  if (plan.stack16) { if (plan.k == 7) go(k_conv_tc_stack16<7>); else go(k_conv_tc_stack16<3>); }
   else if (plan.pair && plan.nw16) go(k_conv_tc_pair<7, true, 16>);
   else if (plan.pair) { if (K == 7 && plan.triple) go(k_conv_tc_pair<7, true>); else if (K == 7) go(k_conv_tc_pair<7>); else go(k_conv_tc_pair<3>); }
   else if (plan.kw == 1 && K > 1) {  // window-folded first layer (K x 1)
@@ -1222,6 +1224,7 @@ void conv_tc_dispatch(const ConvTcPlan& plan, cudaStream_t s, bool configure) {
 }  // namespace
 
 namespace {
+void conv_tc_use_stack16(ConvTcPlan& plan, int K);  // below
 // Output rows per accumulator stage.  4 rows share each weight tile (TMEM: 2 stages x rows x n_tile <= 512 columns), but
 // a layer too small to give every SM a 4-row block runs 2-row blocks instead: twice the CTAs, half the work each.
 int tc_rows(int K, bool roll, int n_tile, int columns = 1 << 30, int H = 1 << 20) {
@@ -1397,6 +1400,21 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   plan->kw = KW;
   plan->roll = roll;
   plan->rows = rows;
+  const char* stack_env = std::getenv("SIVO_B200_STACK16");
+  if (roll && !op.fold_kw && !op.split && p.out_f32 == 1 && (K == 3 || K == 7) && op.cin == 64 && op.cout <= 16 &&
+      op.h_w_raw.size() == static_cast<size_t>(op.cout) * 64 * K * K && !(stack_env && stack_env[0] == '0')) {
+    // the float logits layer (Standard: conv1_1_D, 64 -> 15, 3x3): all K tap rows stacked along N on the full-stack kernel
+    std::vector<__half> w(static_cast<size_t>(K) * K * 16 * 64, __float2half_rn(0.f));
+    for (int o = 0; o < op.cout; ++o)
+      for (int i = 0; i < 64; ++i)
+        for (int kh = 0; kh < K; ++kh)
+          for (int kw = 0; kw < K; ++kw)
+            w[((static_cast<size_t>(kw) * K + kh) * 16 + o) * 64 + i] =
+                __float2half_rn(op.h_w_raw[((static_cast<size_t>(o) * 64 + i) * K + kh) * K + kw]);
+    plan->w_replicas.alloc(w.size() * sizeof(__half));
+    SIVO_CUDA(cudaMemcpy(plan->w_replicas.p, w.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    conv_tc_use_stack16(*plan, K);
+  }
   conv_tc_dispatch(*plan, nullptr, true);
   return plan;
 }
@@ -1472,6 +1490,32 @@ void conv_tc_set_classifier(ConvTcPlan& plan, const float* w_cin_by_cout, int st
   plan.p.cls_out = logits;
 }
 
+namespace {
+// Points a plan whose weights sit in plan.w_replicas as [kw][kh][16][64] half at the full-stack kernel (k_conv_tc_stack16<K>).
+void conv_tc_use_stack16(ConvTcPlan& plan, int K) {
+  TcParams& p = plan.p;
+  cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(K) * K * 16, 1};
+  cuuint64_t strides[2] = {128, static_cast<cuuint64_t>(K) * K * 16 * 128};
+  cuuint32_t box_s[3] = {64, static_cast<cuuint32_t>(K * 16), 1};  // one box per tap column: K taps x 16 rows
+  encode(&plan.map_b, plan.w_replicas.p, 3, dims, strides, box_s);
+  plan.stack16 = true;
+  plan.pair = plan.triple = plan.nw16 = false;
+  const int total_blocks = ceil_div(p.H, kStackRows);
+  const int columns = p.strips * p.N_batch;
+  int ppc = 1;
+  double best_cost = 1e30;
+  for (int c = 1; c <= std::min(total_blocks, 24); ++c) {  // (waves of 148 SMs) x (blocks per CTA + weight load / prologue)
+    const long ctas = static_cast<long>(columns) * ceil_div(total_blocks, c);
+    const double cost = static_cast<double>((ctas + 147) / 148) * (c + 0.35);
+    if (cost < best_cost - 1e-9) { best_cost = cost; ppc = c; }
+  }
+  p.pairs_per_cta = ppc;
+  plan.grid = dim3(p.strips * ceil_div(total_blocks, ppc), 1, p.N_batch);
+  const size_t wbytes = (static_cast<size_t>(K) * K * 16 * 128 + 1023) & ~static_cast<size_t>(1023);
+  plan.smem = 1024 + wbytes + static_cast<size_t>(kStackSlots) * kSlotBytes + (2 * kStackSlots + 1 + 4) * 8 + 16;
+}
+}  // namespace
+
 bool conv_tc_can_compose_classifier(const ConvTcPlan& plan) {
   return plan.pair && plan.triple && plan.k == 7 && !plan.p.out_f32 && !plan.p.unpool_mask && !plan.p.has_drop && !plan.p.pool_out &&
          !plan.p.has_cls && !plan.p.relu && !plan.p.has_bn && plan.p.cout_total == 64;
@@ -1513,22 +1557,7 @@ void conv_tc_set_composed_classifier(ConvTcPlan& plan, const Op& conv, const flo
   p.w_rep = 1;
   const char* stack_env = std::getenv("SIVO_B200_STACK16");
   if (!(stack_env && stack_env[0] == '0')) {
-    // full-stack kernel: one weight box per tap column {64 cin, 7 taps x 16 rows}, 16-row blocks
-    cuuint32_t box_s[3] = {64, 7 * 16, 1};
-    encode(&plan.map_b, plan.w_replicas.p, 3, dims, strides, box_s);
-    plan.stack16 = true;
-    const int total_blocks = ceil_div(p.H, kStackRows);
-    const int columns = p.strips * p.N_batch;
-    int ppc = 1;
-    double best_cost = 1e30;
-    for (int c = 1; c <= std::min(total_blocks, 24); ++c) {  // (waves of 148 SMs) x (blocks per CTA + weight load / prologue)
-      const long ctas = static_cast<long>(columns) * ceil_div(total_blocks, c);
-      const double cost = static_cast<double>((ctas + 147) / 148) * (c + 0.35);
-      if (cost < best_cost - 1e-9) { best_cost = cost; ppc = c; }
-    }
-    p.pairs_per_cta = ppc;
-    plan.grid = dim3(p.strips * ceil_div(total_blocks, ppc), 1, p.N_batch);
-    plan.smem = 1024 + static_cast<size_t>(7) * 7 * 16 * 128 + static_cast<size_t>(kStackSlots) * kSlotBytes + (2 * kStackSlots + 1 + 4) * 8 + 16;
+    conv_tc_use_stack16(plan, K);
   } else {
     p.b_stages = 6;
     plan.nw16 = true;

@@ -36,6 +36,22 @@ struct OrbLevelTable {
   OrbLevel lv[kOrbMaxLevels];
 };
 
+// device quad tree (orb_tree.cu): shared-memory caps of one level
+constexpr int kTreeKeyCap = 8192;   // FAST candidates of one level
+constexpr int kTreeNodeCap = 4096;  // nodes ever created for one level
+constexpr int kTreeListCap = 2048;  // list length / children of one round
+constexpr int kTreeSelCap = 1024;   // retained keypoints of one level (<= n_target + 2)
+
+struct OrbTreeParams {
+  int n_target[kOrbMaxLevels];  // mnFeaturesPerLevel
+  int n_ini[kOrbMaxLevels];     // initial cells: round(width / height) of the level's FAST region (ORBextractor.cc:551)
+  int height[kOrbMaxLevels];    // maxY - minY
+  float hx[kOrbMaxLevels];      // width / n_ini
+  float scale[kOrbMaxLevels];   // mvScaleFactor
+  float size[kOrbMaxLevels];    // float(int(PATCH_SIZE * mvScaleFactor[level]))
+  int min_b;                    // EDGE_THRESHOLD - 3: level coordinate of candidate (0, 0)
+};
+
 struct OrbSelected {  // one retained keypoint, level coordinates
   short x, y;
   short level;
@@ -56,6 +72,15 @@ void orb_launch_compact(const OrbLevelTable& t, const OrbCell* cells, int ncells
 void orb_launch_blur(const uint8_t* pyr, uint8_t* blur, const OrbLevelTable& t, cudaStream_t s);
 void orb_launch_describe(const uint8_t* pyr, const uint8_t* blur, const OrbLevelTable& t, const OrbSelected* sel, int n,
                          const int* umax, float* angles, uint8_t* desc, cudaStream_t s);
+// the same for a keypoint count that lives on the device (<= cap): angles go straight into the keypoint records
+void orb_launch_describe_dev(const uint8_t* pyr, const uint8_t* blur, const OrbLevelTable& t, const OrbSelected* sel, const int* n_dev,
+                             int cap, const int* umax, sivo_keypoint* kps, uint8_t* desc, cudaStream_t s);
+// DistributeOctTree on the device, one block per level (orb_tree.cu), then the level-major keypoint records
+void orb_launch_distribute(const uint32_t* cand, const int* level_off, const OrbTreeParams& prm, int nlevels, uint32_t* sel_packed,
+                           int* level_count, int* error, cudaStream_t s);
+void orb_launch_finalize(const uint32_t* sel_packed, const int* level_count, const OrbTreeParams& prm, int nlevels, int cap,
+                         OrbSelected* sel, sivo_keypoint* kps, int* n_out, long long* n_out_i64, int* error, cudaStream_t s);
+void orb_tree_configure();  // raises k_distribute's dynamic shared-memory limit on the current device
 void orb_upload_pattern();  // copies the rBRIEF pair table into constant memory (once per device)
 
 // ---- host (orb_host.cu)
@@ -86,11 +111,28 @@ class Orb {
   bool has_run() const { return rows_ > 0; }
   int nlevels() const { return nlevels_; }
   void candidates(int level, int* xs, int* ys, int* resp, int cap, int* n) const;
+  // Fully asynchronous form (needs the device quad tree): enqueues the whole extractor on this handle's stream and returns.
+  // Results stay on the device: kps_dev (>= capacity() records), desc_dev (capacity() x 32 bytes), *count_dev (int64).
+  void enqueue_device(const uint8_t* gray_dev, int rows, int cols, size_t pitch, sivo_keypoint* kps_dev, uint8_t* desc_dev,
+                      long long* count_dev);
+  // makes `consumer` wait (on the device) for everything enqueued on this handle's stream so far
+  void stream_wait(cudaStream_t consumer);
+  // bit l set: level l of the last enqueue_device() did not fit the device tree (the results are then not valid)
+  int device_tree_status();
+  int capacity() const { return sel_cap_; }
+  bool device_tree() const { return device_tree_; }
   float device_ms = 0, tree_ms = 0;
   int launches = 0;
 
  private:
   void ensure(int rows, int cols);
+  void enqueue_front(const uint8_t* src, size_t src_pitch, cudaStream_t s);
+  void enqueue_tree_and_describe(sivo_keypoint* kps_dev, uint8_t* desc_dev, long long* count_dev, cudaStream_t s);
+  bool device_tree_ = true;
+  OrbTreeParams tree_prm_{};
+  DevBuf d_sel_packed_, d_level_count_, d_n_err_, d_kps_;
+  PinnedBuf h_n_err_, h_kps_;
+  cudaEvent_t ev_wait_ = nullptr;
   int nfeatures_, nlevels_, ini_th_, min_th_, device_;
   float scale_factor_;
   OrbTables tab_;
@@ -104,8 +146,8 @@ class Orb {
   PinnedBuf h_gray_, h_cand_, h_level_off_, h_sel_, h_angles_, h_desc_, h_pyr_;
   size_t pyr_bytes_ = 0, flat_bytes_ = 0;
   int cand_cap_ = 0, sel_cap_ = 0;
-  std::vector<uint32_t> last_cand_;  // last call's packed candidates (x | y << 12 | resp << 24), all levels (test hook)
-  std::vector<int> last_off_;        // per-level offsets into last_cand_
+  mutable std::vector<uint32_t> last_cand_;  // last call's packed candidates (x | y << 12 | resp << 24), all levels (test hook)
+  mutable std::vector<int> last_off_;        // per-level offsets into last_cand_
   // host quad tree: the pyramid levels are independent, so they are distributed over a few persistent helper threads
   // (largest level first); results are assembled in level order, so the output is the sequential one
   struct TreePool;

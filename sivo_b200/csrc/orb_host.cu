@@ -316,6 +316,23 @@ Orb::Orb(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th,
   h_sel_.ensure(sel_cap_ * sizeof(OrbSelected));
   h_angles_.ensure(sel_cap_ * sizeof(float));
   h_desc_.ensure(static_cast<size_t>(sel_cap_) * 32);
+  {
+    // device quad tree (orb_tree.cu): default; the host tree remains for inputs beyond its shared-memory caps and as the
+    // cross-check in the tests (SIVO_B200_ORB_DEVICE_TREE=0 forces it)
+    const char* e = std::getenv("SIVO_B200_ORB_DEVICE_TREE");
+    device_tree_ = !(e && e[0] == '0');
+    for (int l = 0; l < nlevels; ++l) if (tab_.per_level[l] + 8 > kTreeSelCap) device_tree_ = false;
+    if (device_tree_) {
+      orb_tree_configure();
+      d_sel_packed_.alloc(static_cast<size_t>(kOrbMaxLevels) * kTreeSelCap * sizeof(uint32_t));
+      d_level_count_.alloc(kOrbMaxLevels * sizeof(int));
+      d_n_err_.alloc(2 * sizeof(int));
+      d_kps_.alloc(static_cast<size_t>(sel_cap_) * sizeof(sivo_keypoint));
+      h_n_err_.ensure(2 * sizeof(int));
+      h_kps_.ensure(static_cast<size_t>(sel_cap_) * sizeof(sivo_keypoint));
+      SIVO_CUDA(cudaEventCreateWithFlags(&ev_wait_, cudaEventDisableTiming));
+    }
+  }
   d_level_off_.alloc((kOrbMaxLevels + 1) * sizeof(int));
   h_level_off_.ensure((kOrbMaxLevels + 1) * sizeof(int));
 }
@@ -323,6 +340,7 @@ Orb::Orb(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th,
 Orb::~Orb() {
   cudaSetDevice(device_);
   for (auto& e : ev_) if (e) cudaEventDestroy(e);
+  if (ev_wait_) cudaEventDestroy(ev_wait_);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -356,6 +374,17 @@ void Orb::ensure(int rows, int cols) {
     flat_off = (flat_off + 255) / 256 * 256;
     // cell grid of ComputeKeyPointsOctTree (:759-791)
     const int min_bx = kEdge - 3, min_by = kEdge - 3, max_bx = lv.w - kEdge + 3, max_by = lv.h - kEdge + 3;
+    {  // DistributeOctTree's geometry for this level (:547-551), as orb_distribute derives it
+      int n_ini = static_cast<int>(std::round(static_cast<float>(max_bx - min_bx) / (max_by - min_by)));
+      if (n_ini < 1) n_ini = 1;
+      tree_prm_.n_target[l] = tab_.per_level[l];
+      tree_prm_.n_ini[l] = n_ini;
+      tree_prm_.height[l] = max_by - min_by;
+      tree_prm_.hx[l] = static_cast<float>(max_bx - min_bx) / n_ini;
+      tree_prm_.scale[l] = tab_.scale[l];
+      tree_prm_.size[l] = static_cast<float>(static_cast<int>(31 * tab_.scale[l]));
+      tree_prm_.min_b = kEdge - 3;
+    }
     const float width = static_cast<float>(max_bx - min_bx), height = static_cast<float>(max_by - min_by);
     const int n_cols = static_cast<int>(width / 30.f), n_rows = static_cast<int>(height / 30.f);
     const int w_cell = static_cast<int>(std::ceil(width / n_cols)), h_cell = static_cast<int>(std::ceil(height / n_rows));
@@ -408,7 +437,6 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
   const auto w0 = std::chrono::steady_clock::now();
   SIVO_CUDA(cudaSetDevice(device_));
   ensure(rows, cols);
-  const int ncells = static_cast<int>(cells_.size());
   cudaStream_t s = stream_;
   const uint8_t* src = gray;
   size_t src_pitch = stride;
@@ -427,31 +455,72 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
   } else {
     SIVO_CUDA(cudaEventRecord(ev_[0], s));
   }
-  orb_launch_pyramid(src, rows, cols, src_pitch, d_pyr_.as<uint8_t>(), lt_, s);
-  orb_launch_score(d_pyr_.as<uint8_t>(), d_score_.as<uint8_t>(), lt_, std::min(ini_th_, min_th_), s);
-  orb_launch_cells(d_score_.as<uint8_t>(), lt_, d_cells_.as<OrbCell>(), ncells, ini_th_, min_th_, d_cell_count_.as<int>(),
-                   d_cell_items_.as<uint32_t>(), s);
-  orb_launch_compact(lt_, d_cells_.as<OrbCell>(), ncells, d_cell_count_.as<int>(), d_cell_items_.as<uint32_t>(),
-                     d_cell_offset_.as<int>(), d_level_off_.as<int>(), d_cand_.as<uint32_t>(), cand_cap_, s);
+  enqueue_front(src, src_pitch, s);
+  bool pyr_direct = pyr_out != nullptr;
+  if (pyr_out)
+    for (int l = 0; l < nlevels_; ++l) pyr_direct = pyr_direct && pyr_out[l] && is_pinned_host(pyr_out[l]);
+  auto enqueue_pyramid_readback = [&] {
+    if (pyr_out && pyr_direct) {  // page-locked level buffers (mvImagePyramid storage): strided copies straight into them
+      for (int l = 0; l < nlevels_; ++l) {
+        const OrbLevel& lv = lt_.lv[l];
+        const size_t dst_stride = pyr_strides ? pyr_strides[l] : static_cast<size_t>(lv.w + 2 * kEdge);
+        if (dst_stride < static_cast<size_t>(lv.w + 2 * kEdge)) fail(SIVO_EINVAL, "pyramid stride %zu too small for level %d", dst_stride, l);
+        SIVO_CUDA(cudaMemcpy2DAsync(pyr_out[l], dst_stride, d_pyr_.as<uint8_t>() + lv.img_off, lv.pitch, lv.w + 2 * kEdge,
+                                    lv.h + 2 * kEdge, cudaMemcpyDeviceToHost, s));
+      }
+    } else if (pyr_out) {
+      SIVO_CUDA(cudaMemcpyAsync(h_pyr_.p, d_pyr_.p, pyr_bytes_, cudaMemcpyDeviceToHost, s));
+    }
+  };
+  auto copy_out_pyramid = [&] {
+    if (!(pyr_out && !pyr_direct)) return;
+    for (int l = 0; l < nlevels_; ++l) {
+      if (!pyr_out[l]) continue;
+      const OrbLevel& lv = lt_.lv[l];
+      const size_t dst_stride = pyr_strides ? pyr_strides[l] : static_cast<size_t>(lv.w + 2 * kEdge);
+      if (dst_stride < static_cast<size_t>(lv.w + 2 * kEdge)) fail(SIVO_EINVAL, "pyramid stride %zu too small for level %d", dst_stride, l);
+      const uint8_t* srcl = h_pyr_.as<uint8_t>() + lv.img_off;
+      for (int y = 0; y < lv.h + 2 * kEdge; ++y)
+        memcpy(pyr_out[l] + static_cast<size_t>(y) * dst_stride, srcl + static_cast<size_t>(y) * lv.pitch, lv.w + 2 * kEdge);
+    }
+  };
+  bool pyramid_enqueued = false;
+  if (device_tree_) {
+    // ---- device quad tree: one asynchronous chain, one synchronisation at the end
+    SIVO_CUDA(cudaEventRecord(ev_[1], s));
+    enqueue_tree_and_describe(d_kps_.as<sivo_keypoint>(), d_desc_.as<uint8_t>(), nullptr, s);
+    SIVO_CUDA(cudaEventRecord(ev_[2], s));
+    SIVO_CUDA(cudaMemcpyAsync(h_n_err_.p, d_n_err_.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    SIVO_CUDA(cudaMemcpyAsync(h_kps_.p, d_kps_.p, static_cast<size_t>(sel_cap_) * sizeof(sivo_keypoint), cudaMemcpyDeviceToHost, s));
+    SIVO_CUDA(cudaMemcpyAsync(h_desc_.p, d_desc_.p, static_cast<size_t>(sel_cap_) * 32, cudaMemcpyDeviceToHost, s));
+    SIVO_CUDA(cudaEventRecord(ev_[3], s));
+    enqueue_pyramid_readback();
+    pyramid_enqueued = true;
+    launches = nlevels_ + 8;
+    SIVO_CUDA(cudaStreamSynchronize(s));
+    const int total = h_n_err_.as<int>()[0], err = h_n_err_.as<int>()[1];
+    if (!err) {
+      float a = 0, b2 = 0;
+      SIVO_CUDA(cudaEventElapsedTime(&a, ev_[0], ev_[1]));
+      SIVO_CUDA(cudaEventElapsedTime(&b2, ev_[1], ev_[3]));
+      device_ms = a + b2;
+      tree_ms = 0.f;
+      last_off_.clear();  // candidates() fetches them from the device on demand
+      if (n) *n = total;
+      if (total > cap) fail(SIVO_ERANGE, "ORBextractor: %d keypoints but the caller's buffers hold %d", total, cap);
+      if (kps && total) memcpy(kps, h_kps_.p, static_cast<size_t>(total) * sizeof(sivo_keypoint));
+      if (desc && total) memcpy(desc, h_desc_.p, static_cast<size_t>(total) * 32);
+      copy_out_pyramid();
+      return;
+    }
+    // a level exceeded the device tree's caps: take the host path below (the candidates are still on the device)
+  }
   SIVO_CUDA(cudaMemcpyAsync(h_level_off_.p, d_level_off_.p, (nlevels_ + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
   SIVO_CUDA(cudaMemcpyAsync(h_cand_.p, d_cand_.p, static_cast<size_t>(cand_cap_) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   SIVO_CUDA(cudaEventRecord(ev_[1], s));
   // the blur and the pyramid read-back overlap the host quad tree
   orb_launch_blur(d_pyr_.as<uint8_t>(), d_blur_.as<uint8_t>(), lt_, s);
-  bool pyr_direct = pyr_out != nullptr;
-  if (pyr_out)
-    for (int l = 0; l < nlevels_; ++l) pyr_direct = pyr_direct && pyr_out[l] && is_pinned_host(pyr_out[l]);
-  if (pyr_out && pyr_direct) {  // page-locked level buffers (mvImagePyramid storage): strided copies straight into them
-    for (int l = 0; l < nlevels_; ++l) {
-      const OrbLevel& lv = lt_.lv[l];
-      const size_t dst_stride = pyr_strides ? pyr_strides[l] : static_cast<size_t>(lv.w + 2 * kEdge);
-      if (dst_stride < static_cast<size_t>(lv.w + 2 * kEdge)) fail(SIVO_EINVAL, "pyramid stride %zu too small for level %d", dst_stride, l);
-      SIVO_CUDA(cudaMemcpy2DAsync(pyr_out[l], dst_stride, d_pyr_.as<uint8_t>() + lv.img_off, lv.pitch, lv.w + 2 * kEdge,
-                                  lv.h + 2 * kEdge, cudaMemcpyDeviceToHost, s));
-    }
-  } else if (pyr_out) {
-    SIVO_CUDA(cudaMemcpyAsync(h_pyr_.p, d_pyr_.p, pyr_bytes_, cudaMemcpyDeviceToHost, s));
-  }
+  if (!pyramid_enqueued) enqueue_pyramid_readback();
   launches = nlevels_ + 5;
   static const bool trace = [] { const char* e = std::getenv("SIVO_B200_ORB_TRACE"); return e && e[0] == '1'; }();
   const auto w1 = std::chrono::steady_clock::now();
@@ -562,20 +631,71 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
     if (kps) kps[i] = kp;
   }
   if (desc && total) memcpy(desc, h_desc_.p, static_cast<size_t>(total) * 32);
-  if (pyr_out && !pyr_direct) {
-    for (int l = 0; l < nlevels_; ++l) {
-      if (!pyr_out[l]) continue;
-      const OrbLevel& lv = lt_.lv[l];
-      const size_t dst_stride = pyr_strides ? pyr_strides[l] : static_cast<size_t>(lv.w + 2 * kEdge);
-      if (dst_stride < static_cast<size_t>(lv.w + 2 * kEdge)) fail(SIVO_EINVAL, "pyramid stride %zu too small for level %d", dst_stride, l);
-      const uint8_t* src = h_pyr_.as<uint8_t>() + lv.img_off;
-      for (int y = 0; y < lv.h + 2 * kEdge; ++y)
-        memcpy(pyr_out[l] + static_cast<size_t>(y) * dst_stride, src + static_cast<size_t>(y) * lv.pitch, lv.w + 2 * kEdge);
-    }
-  }
+  copy_out_pyramid();
+}
+
+void Orb::enqueue_front(const uint8_t* src, size_t src_pitch, cudaStream_t s) {
+  const int ncells = static_cast<int>(cells_.size());
+  orb_launch_pyramid(src, rows_, cols_, src_pitch, d_pyr_.as<uint8_t>(), lt_, s);
+  orb_launch_score(d_pyr_.as<uint8_t>(), d_score_.as<uint8_t>(), lt_, std::min(ini_th_, min_th_), s);
+  orb_launch_cells(d_score_.as<uint8_t>(), lt_, d_cells_.as<OrbCell>(), ncells, ini_th_, min_th_, d_cell_count_.as<int>(),
+                   d_cell_items_.as<uint32_t>(), s);
+  orb_launch_compact(lt_, d_cells_.as<OrbCell>(), ncells, d_cell_count_.as<int>(), d_cell_items_.as<uint32_t>(),
+                     d_cell_offset_.as<int>(), d_level_off_.as<int>(), d_cand_.as<uint32_t>(), cand_cap_, s);
+}
+
+void Orb::enqueue_tree_and_describe(sivo_keypoint* kps_dev, uint8_t* desc_dev, long long* count_dev, cudaStream_t s) {
+  int* n_dev = d_n_err_.as<int>();
+  SIVO_CUDA(cudaMemsetAsync(n_dev, 0, 2 * sizeof(int), s));
+  orb_launch_distribute(d_cand_.as<uint32_t>(), d_level_off_.as<int>(), tree_prm_, nlevels_, d_sel_packed_.as<uint32_t>(),
+                        d_level_count_.as<int>(), n_dev + 1, s);
+  orb_launch_finalize(d_sel_packed_.as<uint32_t>(), d_level_count_.as<int>(), tree_prm_, nlevels_, sel_cap_, d_sel_.as<OrbSelected>(),
+                      kps_dev, n_dev, count_dev, n_dev + 1, s);
+  orb_launch_blur(d_pyr_.as<uint8_t>(), d_blur_.as<uint8_t>(), lt_, s);
+  orb_launch_describe_dev(d_pyr_.as<uint8_t>(), d_blur_.as<uint8_t>(), lt_, d_sel_.as<OrbSelected>(), n_dev, sel_cap_,
+                          d_umax_.as<int>(), kps_dev, desc_dev, s);
+}
+
+void Orb::enqueue_device(const uint8_t* gray_dev, int rows, int cols, size_t pitch, sivo_keypoint* kps_dev, uint8_t* desc_dev,
+                         long long* count_dev) {
+  if (!device_tree_) fail(SIVO_EINVAL, "ORBextractor: the asynchronous form needs the device quad tree");
+  if (!gray_dev || !kps_dev || !desc_dev || rows <= 0 || cols <= 0 || pitch < static_cast<size_t>(cols))
+    fail(SIVO_EINVAL, "ORBextractor: bad arguments");
+  SIVO_CUDA(cudaSetDevice(device_));
+  ensure(rows, cols);
+  enqueue_front(gray_dev, pitch, stream_);
+  enqueue_tree_and_describe(kps_dev, desc_dev, count_dev, stream_);
+  launches = nlevels_ + 8;
+  last_off_.clear();
+}
+
+void Orb::stream_wait(cudaStream_t consumer) {
+  if (!ev_wait_) SIVO_CUDA(cudaEventCreateWithFlags(&ev_wait_, cudaEventDisableTiming));
+  SIVO_CUDA(cudaSetDevice(device_));
+  SIVO_CUDA(cudaEventRecord(ev_wait_, stream_));
+  SIVO_CUDA(cudaStreamWaitEvent(consumer, ev_wait_, 0));
+}
+
+int Orb::device_tree_status() {
+  if (!device_tree_) return 0;
+  SIVO_CUDA(cudaSetDevice(device_));
+  int v[2] = {0, 0};
+  SIVO_CUDA(cudaMemcpyAsync(v, d_n_err_.p, sizeof v, cudaMemcpyDeviceToHost, stream_));
+  SIVO_CUDA(cudaStreamSynchronize(stream_));
+  return v[1];
 }
 
 void Orb::candidates(int level, int* xs, int* ys, int* resp, int cap, int* n) const {
+  if (last_off_.empty() && rows_ > 0) {  // device-tree runs leave the candidates on the device: fetch them on demand
+    SIVO_CUDA(cudaSetDevice(device_));
+    last_off_.resize(nlevels_ + 1);
+    SIVO_CUDA(cudaMemcpyAsync(last_off_.data(), d_level_off_.p, (nlevels_ + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    SIVO_CUDA(cudaStreamSynchronize(stream_));
+    const int total = std::min(last_off_[nlevels_], cand_cap_);
+    last_cand_.resize(std::max(total, 1));
+    SIVO_CUDA(cudaMemcpyAsync(last_cand_.data(), d_cand_.p, static_cast<size_t>(total) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+    SIVO_CUDA(cudaStreamSynchronize(stream_));
+  }
   if (level < 0 || level + 1 >= static_cast<int>(last_off_.size())) fail(SIVO_EINVAL, "no candidates for level %d", level);
   const uint32_t* v = last_cand_.data() + last_off_[level];
   const int m = last_off_[level + 1] - last_off_[level];

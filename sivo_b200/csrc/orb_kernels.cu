@@ -292,10 +292,13 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 // ---- one warp per keypoint: IC_Angle (ORBextractor.cc:75-100) then computeOrbDescriptor (:104-150).
+// n_dev != nullptr: the keypoint count lives on the device (device quad tree) and the angle goes into the keypoint record
 __global__ void k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, OrbLevelTable t,
                            const OrbSelected* __restrict__ sel, int n, const int* __restrict__ umax,
-                           float* __restrict__ angles, uint8_t* __restrict__ desc) {
+                           float* __restrict__ angles, uint8_t* __restrict__ desc, const int* __restrict__ n_dev,
+                           sivo_keypoint* __restrict__ kps) {
   int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n_dev) n = min(n, *n_dev);
   if (wid >= n) return;
   const OrbSelected kp = sel[wid];
   const OrbLevel lv = t.lv[kp.level];
@@ -319,7 +322,7 @@ __global__ void k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __res
     m01 += __shfl_xor_sync(0xffffffffu, m01, o);
   }
   const float angle = fast_atan2_deg(static_cast<float>(m01), static_cast<float>(m10));
-  if (lane == 0) angles[wid] = angle;
+  if (lane == 0) { if (kps) kps[wid].angle = angle; else angles[wid] = angle; }
   // rotated BRIEF: lane = descriptor byte
   const float factor_pi = static_cast<float>(3.141592653589793238462643383279502884 / 180.f);
   const float ang = __fmul_rn(angle, factor_pi);
@@ -393,7 +396,14 @@ void orb_launch_blur(const uint8_t* pyr, uint8_t* blur, const OrbLevelTable& t, 
 void orb_launch_describe(const uint8_t* pyr, const uint8_t* blur, const OrbLevelTable& t, const OrbSelected* sel, int n,
                          const int* umax, float* angles, uint8_t* desc, cudaStream_t s) {
   if (n == 0) return;
-  k_describe<<<ceil_div(n * 32, 128), 128, 0, s>>>(pyr, blur, t, sel, n, umax, angles, desc);
+  k_describe<<<ceil_div(n * 32, 128), 128, 0, s>>>(pyr, blur, t, sel, n, umax, angles, desc, nullptr, nullptr);
+  SIVO_CUDA(cudaGetLastError());
+}
+
+void orb_launch_describe_dev(const uint8_t* pyr, const uint8_t* blur, const OrbLevelTable& t, const OrbSelected* sel, const int* n_dev,
+                             int cap, const int* umax, sivo_keypoint* kps, uint8_t* desc, cudaStream_t s) {
+  if (cap == 0) return;
+  k_describe<<<ceil_div(cap * 32, 128), 128, 0, s>>>(pyr, blur, t, sel, cap, umax, nullptr, desc, n_dev, kps);
   SIVO_CUDA(cudaGetLastError());
 }
 

@@ -101,6 +101,25 @@ class ORBextractor:
                                                   desc.ctypes.data_as(C.c_void_p)))
         return kps[:n.value], desc[:n.value]
 
+    def capacity(self) -> int:
+        n = C.c_int()
+        L.check(L.lib().sivo_orb_capacity(self._h, C.byref(n)))
+        return n.value
+
+    def enqueue_device(self, gray_ptr: int, rows: int, cols: int, pitch: int, kps_ptr: int, desc_ptr: int, count_ptr: int):
+        """Asynchronous operator on device-resident buffers (sivo_orb_enqueue_device): returns after the launches are enqueued on
+        the handle's stream; kps / desc / count (int64) stay on the device."""
+        L.check(L.lib().sivo_orb_enqueue_device(self._h, C.c_void_p(gray_ptr), rows, cols, C.c_size_t(pitch), C.c_void_p(kps_ptr),
+                                                C.c_void_p(desc_ptr), C.c_void_p(count_ptr)))
+
+    def stream_wait(self, consumer_stream: int):
+        L.check(L.lib().sivo_orb_stream_wait(self._h, C.c_void_p(consumer_stream)))
+
+    def device_status(self) -> int:
+        m = C.c_int()
+        L.check(L.lib().sivo_orb_device_status(self._h, C.byref(m)))
+        return m.value
+
     def candidates(self, level: int):
         n = C.c_int()
         cap = 1 << 16

@@ -168,3 +168,81 @@ def test_hamming_best2_equals_the_sequential_loop():
     assert np.array_equal(got, want)
     assert np.array_equal(hamming_best2(query, train, off, cand, None)[:, [0, 1, 3]], want[:, [0, 1, 3]])
     assert (got[:5] == np.array([-1, 256, -1, 256, -1])).all()
+
+
+def gpu_tree(xs, ys, rs, min_x, max_x, min_y, max_y, tgt):
+    import ctypes as C
+    from sivo_b200 import _lib as L
+    n = len(xs)
+    cap = 4096
+    ox, oy, orr = (np.empty(cap, np.int32) for _ in range(3))
+    a = [np.ascontiguousarray(v, np.int32) for v in (xs, ys, rs)]
+    rc = L.lib().sivo_dbg_orb_distribute_device(0, a[0].ctypes.data_as(C.c_void_p), a[1].ctypes.data_as(C.c_void_p),
+                                                a[2].ctypes.data_as(C.c_void_p), n, min_x, max_x, min_y, max_y, tgt,
+                                                ox.ctypes.data_as(C.c_void_p), oy.ctypes.data_as(C.c_void_p),
+                                                orr.ctypes.data_as(C.c_void_p), cap)
+    L.check(rc)
+    return ox[:rc].copy(), oy[:rc].copy(), orr[:rc].copy()
+
+
+def test_device_quad_tree_equals_the_host_tree_on_random_inputs():
+    """DistributeOctTree on the device (orb_tree.cu) against the host restatement shared with the oracle: same kept keys in the
+    same ORDER, for inputs that exercise every branch -- a single key, fewer keys than the target, heavy response ties, duplicate
+    positions, the regular rounds stopping on 'no change', and the last one-at-a-time phase."""
+    from sivo_b200.orb import distribute_octtree
+    rng = np.random.default_rng(7)
+    cases = 0
+    for trial in range(60):
+        n = int(rng.integers(1, 6000)) if trial % 5 else int(rng.integers(1, 40))
+        w, h = int(rng.integers(100, 1000)), int(rng.integers(60, 330))
+        xs = rng.integers(0, w, n)
+        ys = rng.integers(0, h, n)
+        if trial % 7 == 0:  # duplicate positions: nodes that cannot be separated
+            xs[: n // 2] = xs[0]
+            ys[: n // 2] = ys[0]
+        rs = rng.integers(7, 30 if trial % 3 else 255, n)
+        tgt = int(rng.integers(1, 500))
+        keep = distribute_octtree(xs.astype(np.float32), ys.astype(np.float32), rs.astype(np.float32), 16, 16 + w, 16, 16 + h, tgt)
+        gx, gy, gr = gpu_tree(xs, ys, rs, 16, 16 + w, 16, 16 + h, tgt)
+        assert len(gx) == len(keep), (trial, n, tgt, len(gx), len(keep))
+        assert np.array_equal(gx, xs[keep]) and np.array_equal(gy, ys[keep]) and np.array_equal(gr, rs[keep]), (trial, n, tgt)
+        cases += 1
+    assert cases == 60
+
+
+def test_device_and_host_quad_tree_give_the_same_extraction(monkeypatch, kitti_gray_crop):
+    """The whole operator with the tree on the device (default: no host round trip) and on the host (SIVO_B200_ORB_DEVICE_TREE=0)."""
+    left, _ = stereo_frame(6)
+    imgs = [kitti_gray_crop, np.ascontiguousarray(bgr_to_gray(left)[11:11 + 352, 109:109 + 1024])]
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SIVO_B200_ORB_DEVICE_TREE", flag)
+        for nf in (2000, 500):
+            ext = ORBextractor(nf, 1.2, 8, 20, 7)
+            res[flag, nf] = [ext(im, None) for im in imgs]
+            assert ext.last_timing()["tree_ms"] == 0.0 if flag == "1" else ext.last_timing()["tree_ms"] > 0.0
+    for nf in (2000, 500):
+        for (ka, da), (kb, db) in zip(res["1", nf], res["0", nf]):
+            assert ka.tobytes() == kb.tobytes() and np.array_equal(da, db)
+
+
+def test_asynchronous_device_form_writes_the_same_record(kitti_gray_crop):
+    """sivo_orb_enqueue_device: gray image, keypoints, descriptors and count all stay on the device (what the multi-GPU record
+    path uses); the results equal the synchronous operator's."""
+    import torch
+    ext = ORBextractor(2000, 1.2, 8, 20, 7)
+    kps, desc = ext(kitti_gray_crop, None)
+    cap = ext.capacity()
+    d_gray = torch.from_numpy(kitti_gray_crop).cuda()
+    d_kps = torch.zeros(cap * 28, dtype=torch.uint8, device="cuda")
+    d_desc = torch.zeros(cap * 32, dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for _ in range(2):
+        ext.enqueue_device(d_gray.data_ptr(), 352, 1024, 1024, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr())
+        ext.stream_wait(torch.cuda.current_stream().cuda_stream)
+        n = int(d_cnt.cpu()[0])
+        assert ext.device_status() == 0
+        assert n == len(kps)
+        got = d_kps.cpu().numpy()[: n * 28].view(KP_DTYPE)
+        assert got.tobytes() == kps.tobytes()
+        assert np.array_equal(d_desc.cpu().numpy()[: n * 32].reshape(n, 32), desc)
