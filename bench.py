@@ -307,9 +307,10 @@ def main():
     h_rec_t = [torch.zeros(rec_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
     h_rec = [t.numpy() for t in h_rec_t]
     stream = torch.cuda.current_stream(dev)
-    side = torch.cuda.Stream(dev) if world > 1 else None
+    side = torch.cuda.Stream(dev)  # joins a frame's three producers; carries the all-gather at N > 1
     ev_main = [torch.cuda.Event() for _ in range(2)]
     ev_side = [torch.cuda.Event() for _ in range(2)]
+    ev_seg = [torch.cuda.Event() for _ in range(2)]
     side_used = [False, False]
 
     prof = {"segnet_launch": 0.0, "orb": 0.0, "pack": 0.0, "gather": 0.0}
@@ -319,41 +320,66 @@ def main():
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(max_workers=2)
 
+    frame_ids = torch.arange(0, 1 << 16, dtype=torch.int64).pin_memory()  # header word 0 of the record, by frame index
+    o_dl, o_kr, o_dr = offs["desc_left"], offs["kp_right"], offs["desc_right"]
+    use_async_orb = orb_l.has_device_tree() and orb_r.has_device_tree() and orb_l.capacity() <= kp_cap
+
     def device_step(i):
+        """One frame with everything resident in HBM and nothing synchronous on the host: SegNet (one graph launch) writes its three
+        maps, the two extractors (asynchronous form, device quad tree) their keypoints / descriptors / counts, all straight into the
+        frame's packed record; at N > 1 the record is all-gathered on a side stream under the next frame's work."""
         j = i % n_frames
         t0 = time.perf_counter()
         k = i & 1
-        if world > 1:
-            if side_used[k]:
-                stream.wait_event(ev_side[k])  # the gather that last read this record has finished
-            base = d_rec[k].data_ptr()
-            seg.run_device(d_bgr[j].data_ptr(), base + o_cls, base + o_conf, base + o_ent, stream.cuda_stream)
-        else:
-            seg.run_device(d_bgr[j].data_ptr(), d_cls.data_ptr(), d_conf.data_ptr(), d_ent.data_ptr(), stream.cuda_stream)
+        base = d_rec[k].data_ptr()
+        # Stream graph of frame i (record k = i & 1); `side` joins the frame and carries the gather:
+        #   main : wait side[k] (frame i-2's record fully consumed) -> SegNet(i) -> seg[k]
+        #   orb_l, orb_r (the handles' own streams): wait side[k] -> extractor(i)
+        #   side : wait seg[k], orb_l, orb_r -> [all-gather of record k] -> side[k]
+        # so the main stream never waits for an extractor and SegNet(i+1) follows SegNet(i) back to back.
+        if side_used[k]:
+            stream.wait_event(ev_side[k])
+            if use_async_orb:
+                orb_l.wait_event(ev_side[k].cuda_event)
+                orb_r.wait_event(ev_side[k].cuda_event)
+        seg.run_device(d_bgr[j].data_ptr(), base + o_cls, base + o_conf, base + o_ent, stream.cuda_stream)
         t1 = time.perf_counter()
-        fr_ = pool.submit(orb_r.run_device_input, d_gr[j].data_ptr(), NET_H, NET_W, NET_W)
-        out = [orb_l.run_device_input(d_gl[j].data_ptr(), NET_H, NET_W, NET_W), None]
-        out[1] = fr_.result()
-        t2 = time.perf_counter()
-        t3 = t2
-        if world > 1:
+        out = None
+        if use_async_orb:
+            orb_l.enqueue_device(d_gl[j].data_ptr(), NET_H, NET_W, NET_W, base + o_kp, base + o_dl, base + 8)
+            orb_r.enqueue_device(d_gr[j].data_ptr(), NET_H, NET_W, NET_W, base + o_kr, base + o_dr, base + 16)
+            d_rec[k][:8].view(torch.int64).copy_(frame_ids[(rank * 4096 + i) & 0xFFFF:][:1], non_blocking=True)
+            t2 = t3 = time.perf_counter()
+        else:  # host quad tree (nfeatures beyond the device tree's capacity): blocking extractor calls, host-packed record
+            fr_ = pool.submit(orb_r.run_device_input, d_gr[j].data_ptr(), NET_H, NET_W, NET_W)
+            out = [orb_l.run_device_input(d_gl[j].data_ptr(), NET_H, NET_W, NET_W), None]
+            out[1] = fr_.result()
+            t2 = time.perf_counter()
             if side_used[k]:
-                ev_main[k].synchronize()  # the upload that last read this pinned buffer (two frames ago) has been consumed
+                ev_seg[k].synchronize()  # the upload that last read this pinned buffer (two frames ago) has been consumed
             record.pack_host_part(h_rec[k], hw, kp_cap, rank * 100000 + i, out[0][0], out[0][1], out[1][0], out[1][1])
             t3 = time.perf_counter()
             d_rec[k][:record.HEADER].copy_(h_rec_t[k][:record.HEADER], non_blocking=True)
             d_rec[k][o_kp:].copy_(h_rec_t[k][o_kp:], non_blocking=True)
-            ev_main[k].record(stream)
-            with torch.cuda.stream(side):
-                side.wait_event(ev_main[k])
+        ev_seg[k].record(stream)
+        with torch.cuda.stream(side):
+            side.wait_event(ev_seg[k])
+            if use_async_orb:
+                orb_l.stream_wait(side.cuda_stream)
+                orb_r.stream_wait(side.cuda_stream)
+            if world > 1:
                 dist.all_gather_into_tensor(d_all[k], d_rec[k])
-                ev_side[k].record(side)
-            side_used[k] = True
+            ev_side[k].record(side)
+        side_used[k] = True
         t4 = time.perf_counter()
         prof["segnet_launch"] += t1 - t0
         prof["orb"] += t2 - t1
         prof["pack"] += t3 - t2
         prof["gather"] += t4 - t3
+        if (i & 3) == 3 and side_used[k ^ 1]:
+            # bounded run-ahead: nothing above waits for the GPU, so without this the host would queue the whole run at once.
+            # Waiting for the PREVIOUS frame keeps one frame queued behind the one that is running (no bubble)
+            ev_side[k ^ 1].synchronize()
         return out
 
     # e2e buffers: page-locked host memory, as the contract asks (inputs from pinned memory; the results land in
@@ -451,8 +477,15 @@ def main():
     e2e_elapsed = e2e_times["reference_order_pinned"]
     clocks = sampler.stop() if rank == 0 else None
     n_kp = len(out[0][0]) + len(out[1][0])
-    h2d = 1242 * 375 * 0 + hw * 3 + 2 * hw + n_kp * 8
-    d2h = hw * 17 + n_kp * 36 + 2 * (32768 * 4 + 9 * 4) + 2 * sum((int(round(NET_H / 1.2 ** l)) + 38) * (int(round(NET_W / 1.2 ** l)) + 38 + 15) for l in range(8))
+    # per step, counted from the copies the three calls make: the cropped colour image and the two gray images go up; the three maps,
+    # per extractor (count + status, the keypoint and descriptor capacity) and the 8 bordered pyramid levels come down
+    pyr_bytes = 2 * sum((int(round(NET_H / 1.2 ** l)) + 38) * (int(round(NET_W / 1.2 ** l)) + 38 + 15) for l in range(8))
+    if orb_l.has_device_tree():
+        h2d = hw * 3 + 2 * hw
+        d2h = hw * 17 + 2 * (8 + orb_l.capacity() * 60) + pyr_bytes
+    else:  # host quad tree: candidates down, selected keypoints up
+        h2d = hw * 3 + 2 * hw + n_kp * 8
+        d2h = hw * 17 + n_kp * 36 + 2 * (32768 * 4 + 9 * 4) + pyr_bytes
     if world > 1:
         names = sorted(e2e_times)
         tt = torch.tensor([elapsed] + [e2e_times[n] for n in names], dtype=torch.float64, device=dev)

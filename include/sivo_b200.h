@@ -136,8 +136,14 @@ int sivo_orb_run_device_input(sivo_orb_t* h, const uint8_t* gray_device, int row
 int sivo_orb_enqueue_device(sivo_orb_t* h, const uint8_t* gray_device, int rows, int cols, size_t pitch, sivo_keypoint* kps_device,
                             uint8_t* desc32_device, long long* count_device);
 int sivo_orb_stream_wait(sivo_orb_t* h, void* consumer_cuda_stream);
+/* The reverse edge: the handle's stream waits for everything enqueued on `producer_cuda_stream` so far (e.g. the collective
+ * that still reads the buffers the next sivo_orb_enqueue_device will overwrite). */
+int sivo_orb_wait_for_stream(sivo_orb_t* h, void* producer_cuda_stream);
+/* The same edge for one recorded event (a cudaEvent_t): the handle's stream waits for exactly that point of another stream. */
+int sivo_orb_wait_event(sivo_orb_t* h, void* cuda_event);
 int sivo_orb_device_status(sivo_orb_t* h, int* level_mask);
 int sivo_orb_capacity(const sivo_orb_t* h, int* max_keypoints);
+int sivo_orb_has_device_tree(const sivo_orb_t* h, int* yes);
 int sivo_orb_level_size(const sivo_orb_t* h, int rows, int cols, int level, int* level_w, int* level_h);
 /* Test hook: FAST candidates of the last run before the quad tree, per level (x, y relative to the
  * (16,16) border origin as in ComputeKeyPointsOctTree, response). */

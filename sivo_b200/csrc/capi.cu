@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -46,6 +47,12 @@ int sivo_segnet_create(const char* prototxt, const char* caffemodel, int device,
   sivo_segnet_options o{};
   o.device = device;
   o.seed = seed;
+  // knobs with no slot in the reference's constructor come from the environment (the C++ shim calls this entry point):
+  // SIVO_B200_PRECISION = fp16 (default: the fast mode) | fp32 (strict: split-operand tensor-core convolutions, fp32 activations);
+  // SIVO_B200_ENGINE = auto | simt | tcgen05
+  if (const char* e = std::getenv("SIVO_B200_PRECISION")) o.precision = (std::string(e) == "fp32") ? SIVO_PRECISION_FP32 : SIVO_PRECISION_FP16;
+  if (const char* e = std::getenv("SIVO_B200_ENGINE"))
+    o.engine = std::string(e) == "simt" ? SIVO_ENGINE_SIMT : std::string(e) == "tcgen05" ? SIVO_ENGINE_TCGEN05 : SIVO_ENGINE_AUTO;
   return sivo_segnet_create_ex(prototxt, caffemodel, &o, out);
 }
 
@@ -209,11 +216,32 @@ int sivo_orb_stream_wait(sivo_orb_t* h, void* consumer_cuda_stream) {
   });
 }
 
+int sivo_orb_wait_for_stream(sivo_orb_t* h, void* producer_cuda_stream) {
+  return guarded([&] {
+    if (!h) fail(SIVO_EINVAL, "null handle");
+    h->impl->wait_for_stream(static_cast<cudaStream_t>(producer_cuda_stream));
+  });
+}
+
+int sivo_orb_wait_event(sivo_orb_t* h, void* cuda_event) {
+  return guarded([&] {
+    if (!h || !cuda_event) fail(SIVO_EINVAL, "null argument");
+    h->impl->wait_event(static_cast<cudaEvent_t>(cuda_event));
+  });
+}
+
 int sivo_orb_device_status(sivo_orb_t* h, int* level_mask) {
   return guarded([&] {
     if (!h) fail(SIVO_EINVAL, "null handle");
     const int m = h->impl->device_tree_status();
     if (level_mask) *level_mask = m;
+  });
+}
+
+int sivo_orb_has_device_tree(const sivo_orb_t* h, int* yes) {
+  return guarded([&] {
+    if (!h) fail(SIVO_EINVAL, "null handle");
+    if (yes) *yes = h->impl->device_tree() ? 1 : 0;
   });
 }
 

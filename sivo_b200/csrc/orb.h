@@ -117,6 +117,8 @@ class Orb {
                       long long* count_dev);
   // makes `consumer` wait (on the device) for everything enqueued on this handle's stream so far
   void stream_wait(cudaStream_t consumer);
+  void wait_for_stream(cudaStream_t producer);
+  void wait_event(cudaEvent_t e);
   // bit l set: level l of the last enqueue_device() did not fit the device tree (the results are then not valid)
   int device_tree_status();
   int capacity() const { return sel_cap_; }
@@ -132,7 +134,7 @@ class Orb {
   OrbTreeParams tree_prm_{};
   DevBuf d_sel_packed_, d_level_count_, d_n_err_, d_kps_;
   PinnedBuf h_n_err_, h_kps_;
-  cudaEvent_t ev_wait_ = nullptr;
+  cudaEvent_t ev_wait_ = nullptr, ev_wait2_ = nullptr;
   int nfeatures_, nlevels_, ini_th_, min_th_, device_;
   float scale_factor_;
   OrbTables tab_;

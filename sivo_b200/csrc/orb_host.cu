@@ -341,6 +341,7 @@ Orb::~Orb() {
   cudaSetDevice(device_);
   for (auto& e : ev_) if (e) cudaEventDestroy(e);
   if (ev_wait_) cudaEventDestroy(ev_wait_);
+  if (ev_wait2_) cudaEventDestroy(ev_wait2_);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -674,6 +675,18 @@ void Orb::stream_wait(cudaStream_t consumer) {
   SIVO_CUDA(cudaSetDevice(device_));
   SIVO_CUDA(cudaEventRecord(ev_wait_, stream_));
   SIVO_CUDA(cudaStreamWaitEvent(consumer, ev_wait_, 0));
+}
+
+void Orb::wait_for_stream(cudaStream_t producer) {
+  SIVO_CUDA(cudaSetDevice(device_));
+  if (!ev_wait2_) SIVO_CUDA(cudaEventCreateWithFlags(&ev_wait2_, cudaEventDisableTiming));
+  SIVO_CUDA(cudaEventRecord(ev_wait2_, producer));
+  SIVO_CUDA(cudaStreamWaitEvent(stream_, ev_wait2_, 0));
+}
+
+void Orb::wait_event(cudaEvent_t e) {
+  SIVO_CUDA(cudaSetDevice(device_));
+  SIVO_CUDA(cudaStreamWaitEvent(stream_, e, 0));
 }
 
 int Orb::device_tree_status() {

@@ -145,6 +145,43 @@ __global__ void k_stereo_match(const sivo_keypoint* __restrict__ kl, const uint8
     sad_dist[wid] = out_sad;
   }
 }
+
+// Per-thread, per-device workspace of the stereo / Hamming entry points: one arena that only grows and one non-blocking stream.
+// (Allocating and freeing half a dozen buffers per call and running on the legacy default stream synchronises the whole device,
+// i.e. serialises every per-frame call against the SegNet graph and the extractors' streams.)
+struct StereoWs {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  DevBuf arena;
+  size_t used = 0;
+  void begin(int dev, size_t bytes_needed) {
+    SIVO_CUDA(cudaSetDevice(dev));
+    if (device != dev) {
+      if (stream) { cudaSetDevice(device); cudaStreamDestroy(stream); cudaSetDevice(dev); }
+      arena.release();
+      SIVO_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+      device = dev;
+    }
+    if (arena.bytes < bytes_needed) {
+      SIVO_CUDA(cudaStreamSynchronize(stream));
+      arena.alloc(bytes_needed + bytes_needed / 2);
+    }
+    used = 0;
+  }
+  template <class T> T* take(size_t count) {
+    used = (used + 255) & ~static_cast<size_t>(255);
+    T* p = reinterpret_cast<T*>(arena.as<uint8_t>() + used);
+    used += std::max<size_t>(count, 1) * sizeof(T);
+    if (used > arena.bytes) fail(SIVO_ENOMEM, "stereo workspace accounting");
+    return p;
+  }
+  ~StereoWs() { if (stream) { cudaSetDevice(device); cudaStreamDestroy(stream); } }
+};
+StereoWs& stereo_ws() {
+  static thread_local StereoWs ws;
+  return ws;
+}
+inline size_t pad256(size_t b) { return (std::max<size_t>(b, 1) + 255) & ~static_cast<size_t>(255); }
 }  // namespace
 
 void stereo_hamming(int device, const sivo_keypoint* left, const uint8_t* dl, int nl, const sivo_keypoint* right,
@@ -154,22 +191,29 @@ void stereo_hamming(int device, const sivo_keypoint* left, const uint8_t* dl, in
   if (nl == 0) return;
   for (int i = 0; i < nl; ++i) if (left[i].octave < 0 || left[i].octave >= nlevels) fail(SIVO_EINVAL, "stereo: left octave out of range");
   for (int i = 0; i < nr; ++i) if (right[i].octave < 0 || right[i].octave >= nlevels) fail(SIVO_EINVAL, "stereo: right octave out of range");
-  SIVO_CUDA(cudaSetDevice(device));
-  DevBuf d_kl(nl * sizeof(sivo_keypoint)), d_dl(static_cast<size_t>(nl) * 32), d_kr(std::max(nr, 1) * sizeof(sivo_keypoint)),
-      d_dr(static_cast<size_t>(std::max(nr, 1)) * 32), d_sc(nlevels * sizeof(float)), d_bi(nl * sizeof(int)), d_bd(nl * sizeof(int));
-  SIVO_CUDA(cudaMemcpy(d_kl.p, left, nl * sizeof(sivo_keypoint), cudaMemcpyHostToDevice));
-  SIVO_CUDA(cudaMemcpy(d_dl.p, dl, static_cast<size_t>(nl) * 32, cudaMemcpyHostToDevice));
+  StereoWs& ws = stereo_ws();
+  ws.begin(device, pad256(nl * sizeof(sivo_keypoint)) + pad256(static_cast<size_t>(nl) * 32) + pad256(nr * sizeof(sivo_keypoint)) +
+                       pad256(static_cast<size_t>(nr) * 32) + pad256(nlevels * sizeof(float)) + 2 * pad256(nl * sizeof(int)) + 4096);
+  cudaStream_t st = ws.stream;
+  sivo_keypoint* d_kl = ws.take<sivo_keypoint>(nl);
+  uint8_t* d_dl = ws.take<uint8_t>(static_cast<size_t>(nl) * 32);
+  sivo_keypoint* d_kr = ws.take<sivo_keypoint>(nr);
+  uint8_t* d_dr = ws.take<uint8_t>(static_cast<size_t>(nr) * 32);
+  float* d_sc = ws.take<float>(nlevels);
+  int* d_bi = ws.take<int>(nl);
+  int* d_bd = ws.take<int>(nl);
+  SIVO_CUDA(cudaMemcpyAsync(d_kl, left, nl * sizeof(sivo_keypoint), cudaMemcpyHostToDevice, st));
+  SIVO_CUDA(cudaMemcpyAsync(d_dl, dl, static_cast<size_t>(nl) * 32, cudaMemcpyHostToDevice, st));
   if (nr) {
-    SIVO_CUDA(cudaMemcpy(d_kr.p, right, nr * sizeof(sivo_keypoint), cudaMemcpyHostToDevice));
-    SIVO_CUDA(cudaMemcpy(d_dr.p, dr, static_cast<size_t>(nr) * 32, cudaMemcpyHostToDevice));
+    SIVO_CUDA(cudaMemcpyAsync(d_kr, right, nr * sizeof(sivo_keypoint), cudaMemcpyHostToDevice, st));
+    SIVO_CUDA(cudaMemcpyAsync(d_dr, dr, static_cast<size_t>(nr) * 32, cudaMemcpyHostToDevice, st));
   }
-  SIVO_CUDA(cudaMemcpy(d_sc.p, scale, nlevels * sizeof(float), cudaMemcpyHostToDevice));
-  k_stereo_hamming<<<ceil_div(nl * 32, 128), 128>>>(d_kl.as<sivo_keypoint>(), d_dl.as<uint8_t>(), nl, d_kr.as<sivo_keypoint>(),
-                                                    d_dr.as<uint8_t>(), nr, d_sc.as<float>(), rows, min_d, max_d,
-                                                    d_bi.as<int>(), d_bd.as<int>());
+  SIVO_CUDA(cudaMemcpyAsync(d_sc, scale, nlevels * sizeof(float), cudaMemcpyHostToDevice, st));
+  k_stereo_hamming<<<ceil_div(nl * 32, 128), 128, 0, st>>>(d_kl, d_dl, nl, d_kr, d_dr, nr, d_sc, rows, min_d, max_d, d_bi, d_bd);
   SIVO_CUDA(cudaGetLastError());
-  SIVO_CUDA(cudaMemcpy(best_idx, d_bi.p, nl * sizeof(int), cudaMemcpyDeviceToHost));
-  SIVO_CUDA(cudaMemcpy(best_dist, d_bd.p, nl * sizeof(int), cudaMemcpyDeviceToHost));
+  SIVO_CUDA(cudaMemcpyAsync(best_idx, d_bi, nl * sizeof(int), cudaMemcpyDeviceToHost, st));
+  SIVO_CUDA(cudaMemcpyAsync(best_dist, d_bd, nl * sizeof(int), cudaMemcpyDeviceToHost, st));
+  SIVO_CUDA(cudaStreamSynchronize(st));
 }
 
 // ---- best / second-best descriptor match over per-query candidate lists: the inner loop shared by
@@ -220,18 +264,25 @@ void hamming_best2(int device, const uint8_t* query, int nq, const uint8_t* trai
   for (int i = 0; i < nq; ++i) if (cand_off[i + 1] < cand_off[i]) fail(SIVO_EINVAL, "hamming_best2: candidate offsets must not decrease");
   const int nc = cand_off[nq];
   for (int i = 0; i < nc; ++i) if (cand_idx[i] < 0 || cand_idx[i] >= nt) fail(SIVO_ERANGE, "hamming_best2: candidate %d names train descriptor %d of %d", i, cand_idx[i], nt);
-  SIVO_CUDA(cudaSetDevice(device));
-  DevBuf d_q(static_cast<size_t>(nq) * 32), d_t(static_cast<size_t>(std::max(nt, 1)) * 32), d_off((nq + 1) * sizeof(int)),
-      d_idx(std::max(nc, 1) * sizeof(int)), d_lvl(std::max(nt, 1) * sizeof(int)), d_out(static_cast<size_t>(nq) * 5 * sizeof(int));
-  SIVO_CUDA(cudaMemcpy(d_q.p, query, static_cast<size_t>(nq) * 32, cudaMemcpyHostToDevice));
-  if (nt) SIVO_CUDA(cudaMemcpy(d_t.p, train, static_cast<size_t>(nt) * 32, cudaMemcpyHostToDevice));
-  SIVO_CUDA(cudaMemcpy(d_off.p, cand_off, (nq + 1) * sizeof(int), cudaMemcpyHostToDevice));
-  if (nc) SIVO_CUDA(cudaMemcpy(d_idx.p, cand_idx, nc * sizeof(int), cudaMemcpyHostToDevice));
-  if (train_level && nt) SIVO_CUDA(cudaMemcpy(d_lvl.p, train_level, nt * sizeof(int), cudaMemcpyHostToDevice));
-  k_hamming_best2<<<ceil_div(nq * 32, 128), 128>>>(d_q.as<uint8_t>(), nq, d_t.as<uint8_t>(), d_off.as<int>(), d_idx.as<int>(),
-                                                   train_level ? d_lvl.as<int>() : nullptr, d_out.as<int>());
+  StereoWs& ws = stereo_ws();
+  ws.begin(device, pad256(static_cast<size_t>(nq) * 32) + pad256(static_cast<size_t>(nt) * 32) + pad256((nq + 1) * sizeof(int)) +
+                       pad256(nc * sizeof(int)) + pad256(nt * sizeof(int)) + pad256(static_cast<size_t>(nq) * 5 * sizeof(int)) + 4096);
+  cudaStream_t st = ws.stream;
+  uint8_t* d_q = ws.take<uint8_t>(static_cast<size_t>(nq) * 32);
+  uint8_t* d_t = ws.take<uint8_t>(static_cast<size_t>(nt) * 32);
+  int* d_off = ws.take<int>(nq + 1);
+  int* d_idx = ws.take<int>(nc);
+  int* d_lvl = ws.take<int>(nt);
+  int* d_out = ws.take<int>(static_cast<size_t>(nq) * 5);
+  SIVO_CUDA(cudaMemcpyAsync(d_q, query, static_cast<size_t>(nq) * 32, cudaMemcpyHostToDevice, st));
+  if (nt) SIVO_CUDA(cudaMemcpyAsync(d_t, train, static_cast<size_t>(nt) * 32, cudaMemcpyHostToDevice, st));
+  SIVO_CUDA(cudaMemcpyAsync(d_off, cand_off, (nq + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (nc) SIVO_CUDA(cudaMemcpyAsync(d_idx, cand_idx, nc * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (train_level && nt) SIVO_CUDA(cudaMemcpyAsync(d_lvl, train_level, nt * sizeof(int), cudaMemcpyHostToDevice, st));
+  k_hamming_best2<<<ceil_div(nq * 32, 128), 128, 0, st>>>(d_q, nq, d_t, d_off, d_idx, train_level ? d_lvl : nullptr, d_out);
   SIVO_CUDA(cudaGetLastError());
-  SIVO_CUDA(cudaMemcpy(out5, d_out.p, static_cast<size_t>(nq) * 5 * sizeof(int), cudaMemcpyDeviceToHost));
+  SIVO_CUDA(cudaMemcpyAsync(out5, d_out, static_cast<size_t>(nq) * 5 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  SIVO_CUDA(cudaStreamSynchronize(st));
 }
 
 }  // namespace sivo
@@ -248,24 +299,34 @@ void stereo_match(const Orb& left, const Orb& right, const sivo_keypoint* kl, co
   const int nlev = left.nlevels();
   for (int i = 0; i < nl; ++i) if (kl[i].octave < 0 || kl[i].octave >= nlev) fail(SIVO_EINVAL, "stereo: left octave out of range");
   for (int i = 0; i < nr; ++i) if (kr[i].octave < 0 || kr[i].octave >= nlev) fail(SIVO_EINVAL, "stereo: right octave out of range");
-  SIVO_CUDA(cudaSetDevice(left.device()));
-  DevBuf d_kl(nl * sizeof(sivo_keypoint)), d_dl(static_cast<size_t>(nl) * 32), d_kr(nr * sizeof(sivo_keypoint)), d_dr(static_cast<size_t>(nr) * 32),
-      d_sc(nlev * sizeof(float)), d_isc(nlev * sizeof(float)), d_u(nl * sizeof(float)), d_z(nl * sizeof(float)), d_s(nl * sizeof(int));
-  SIVO_CUDA(cudaMemcpy(d_kl.p, kl, nl * sizeof(sivo_keypoint), cudaMemcpyHostToDevice));
-  SIVO_CUDA(cudaMemcpy(d_dl.p, dl, static_cast<size_t>(nl) * 32, cudaMemcpyHostToDevice));
-  SIVO_CUDA(cudaMemcpy(d_kr.p, kr, nr * sizeof(sivo_keypoint), cudaMemcpyHostToDevice));
-  SIVO_CUDA(cudaMemcpy(d_dr.p, dr, static_cast<size_t>(nr) * 32, cudaMemcpyHostToDevice));
-  SIVO_CUDA(cudaMemcpy(d_sc.p, left.tables().scale.data(), nlev * sizeof(float), cudaMemcpyHostToDevice));
-  SIVO_CUDA(cudaMemcpy(d_isc.p, left.tables().inv_scale.data(), nlev * sizeof(float), cudaMemcpyHostToDevice));
-  k_stereo_match<<<ceil_div(nl * 32, 128), 128>>>(d_kl.as<sivo_keypoint>(), d_dl.as<uint8_t>(), nl, d_kr.as<sivo_keypoint>(),
-                                                  d_dr.as<uint8_t>(), nr, d_sc.as<float>(), d_isc.as<float>(), left.dev_pyramid(),
-                                                  left.levels(), right.dev_pyramid(), right.levels(), mb, mbf, d_u.as<float>(),
-                                                  d_z.as<float>(), d_s.as<int>());
+  StereoWs& ws = stereo_ws();
+  ws.begin(left.device(), pad256(nl * sizeof(sivo_keypoint)) + pad256(static_cast<size_t>(nl) * 32) + pad256(nr * sizeof(sivo_keypoint)) +
+                              pad256(static_cast<size_t>(nr) * 32) + 2 * pad256(nlev * sizeof(float)) + 3 * pad256(nl * sizeof(float)) + 4096);
+  cudaStream_t st = ws.stream;
+  sivo_keypoint* d_kl = ws.take<sivo_keypoint>(nl);
+  uint8_t* d_dl = ws.take<uint8_t>(static_cast<size_t>(nl) * 32);
+  sivo_keypoint* d_kr = ws.take<sivo_keypoint>(nr);
+  uint8_t* d_dr = ws.take<uint8_t>(static_cast<size_t>(nr) * 32);
+  float* d_sc = ws.take<float>(nlev);
+  float* d_isc = ws.take<float>(nlev);
+  float* d_u = ws.take<float>(nl);
+  float* d_z = ws.take<float>(nl);
+  int* d_s = ws.take<int>(nl);
+  SIVO_CUDA(cudaMemcpyAsync(d_kl, kl, nl * sizeof(sivo_keypoint), cudaMemcpyHostToDevice, st));
+  SIVO_CUDA(cudaMemcpyAsync(d_dl, dl, static_cast<size_t>(nl) * 32, cudaMemcpyHostToDevice, st));
+  SIVO_CUDA(cudaMemcpyAsync(d_kr, kr, nr * sizeof(sivo_keypoint), cudaMemcpyHostToDevice, st));
+  SIVO_CUDA(cudaMemcpyAsync(d_dr, dr, static_cast<size_t>(nr) * 32, cudaMemcpyHostToDevice, st));
+  SIVO_CUDA(cudaMemcpyAsync(d_sc, left.tables().scale.data(), nlev * sizeof(float), cudaMemcpyHostToDevice, st));
+  SIVO_CUDA(cudaMemcpyAsync(d_isc, left.tables().inv_scale.data(), nlev * sizeof(float), cudaMemcpyHostToDevice, st));
+  // the pyramids were written on the two extractors' own streams; their synchronous run() has returned, so they are complete
+  k_stereo_match<<<ceil_div(nl * 32, 128), 128, 0, st>>>(d_kl, d_dl, nl, d_kr, d_dr, nr, d_sc, d_isc, left.dev_pyramid(), left.levels(),
+                                                         right.dev_pyramid(), right.levels(), mb, mbf, d_u, d_z, d_s);
   SIVO_CUDA(cudaGetLastError());
   std::vector<int> sad(nl);
-  SIVO_CUDA(cudaMemcpy(u_right, d_u.p, nl * sizeof(float), cudaMemcpyDeviceToHost));
-  SIVO_CUDA(cudaMemcpy(depth, d_z.p, nl * sizeof(float), cudaMemcpyDeviceToHost));
-  SIVO_CUDA(cudaMemcpy(sad.data(), d_s.p, nl * sizeof(int), cudaMemcpyDeviceToHost));
+  SIVO_CUDA(cudaMemcpyAsync(u_right, d_u, nl * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SIVO_CUDA(cudaMemcpyAsync(depth, d_z, nl * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SIVO_CUDA(cudaMemcpyAsync(sad.data(), d_s, nl * sizeof(int), cudaMemcpyDeviceToHost, st));
+  SIVO_CUDA(cudaStreamSynchronize(st));
   // median-based outlier cut (Frame.cc:617-628)
   std::vector<std::pair<int, int>> v;
   for (int i = 0; i < nl; ++i) if (sad[i] >= 0) v.emplace_back(sad[i], i);

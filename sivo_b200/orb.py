@@ -3,6 +3,7 @@ of `Frame::ComputeStereoMatches` over the C-ABI."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -101,6 +102,12 @@ class ORBextractor:
                                                   desc.ctypes.data_as(C.c_void_p)))
         return kps[:n.value], desc[:n.value]
 
+    def has_device_tree(self) -> bool:
+        """True if this handle distributes on the device (no host round trip; the asynchronous form is available)."""
+        y = C.c_int()
+        L.check(L.lib().sivo_orb_has_device_tree(self._h, C.byref(y)))
+        return bool(y.value)
+
     def capacity(self) -> int:
         n = C.c_int()
         L.check(L.lib().sivo_orb_capacity(self._h, C.byref(n)))
@@ -114,6 +121,12 @@ class ORBextractor:
 
     def stream_wait(self, consumer_stream: int):
         L.check(L.lib().sivo_orb_stream_wait(self._h, C.c_void_p(consumer_stream)))
+
+    def wait_for_stream(self, producer_stream: int):
+        L.check(L.lib().sivo_orb_wait_for_stream(self._h, C.c_void_p(producer_stream)))
+
+    def wait_event(self, cuda_event: int):
+        L.check(L.lib().sivo_orb_wait_event(self._h, C.c_void_p(cuda_event)))
 
     def device_status(self) -> int:
         m = C.c_int()
