@@ -302,16 +302,16 @@ def main():
     o_cls, o_conf, o_ent, o_kp = offs["classes"], offs["confidence"], offs["entropy"], offs["kp_left"]
     # double-buffered: the gather of frame i runs on a side stream under the convolutions of frame i+1.  SegNet writes its
     # three maps straight into the record (no device-to-device packing copies).
-    d_rec = [torch.zeros(rec_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
-    d_all = [torch.empty(rec_bytes * world, dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
-    h_rec_t = [torch.zeros(rec_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    NBUF = 3  # records in flight: frame i reuses the buffers of frame i-3, so a late gather (a late peer) has two frames of slack
+    d_rec = [torch.zeros(rec_bytes, dtype=torch.uint8, device=dev) for _ in range(NBUF)]
+    d_all = [torch.empty(rec_bytes * world, dtype=torch.uint8, device=dev) for _ in range(NBUF)] if world > 1 else None
+    h_rec_t = [torch.zeros(rec_bytes, dtype=torch.uint8).pin_memory() for _ in range(NBUF)]
     h_rec = [t.numpy() for t in h_rec_t]
     stream = torch.cuda.current_stream(dev)
     side = torch.cuda.Stream(dev)  # joins a frame's three producers; carries the all-gather at N > 1
-    ev_main = [torch.cuda.Event() for _ in range(2)]
-    ev_side = [torch.cuda.Event() for _ in range(2)]
-    ev_seg = [torch.cuda.Event() for _ in range(2)]
-    side_used = [False, False]
+    ev_side = [torch.cuda.Event() for _ in range(NBUF)]
+    ev_seg = [torch.cuda.Event() for _ in range(NBUF)]
+    side_used = [False] * NBUF
 
     prof = {"segnet_launch": 0.0, "orb": 0.0, "pack": 0.0, "gather": 0.0}
 
@@ -324,19 +324,23 @@ def main():
     o_dl, o_kr, o_dr = offs["desc_left"], offs["kp_right"], offs["desc_right"]
     use_async_orb = orb_l.has_device_tree() and orb_r.has_device_tree() and orb_l.capacity() <= kp_cap
 
+    JOIN_ON_MAIN = os.environ.get("SIVO_BENCH_JOIN", "main") != "side"  # where a frame's extractors are joined (see device_step)
+
     def device_step(i):
         """One frame with everything resident in HBM and nothing synchronous on the host: SegNet (one graph launch) writes its three
         maps, the two extractors (asynchronous form, device quad tree) their keypoints / descriptors / counts, all straight into the
         frame's packed record; at N > 1 the record is all-gathered on a side stream under the next frame's work."""
         j = i % n_frames
         t0 = time.perf_counter()
-        k = i & 1
+        k = i % NBUF
         base = d_rec[k].data_ptr()
-        # Stream graph of frame i (record k = i & 1); `side` joins the frame and carries the gather:
-        #   main : wait side[k] (frame i-2's record fully consumed) -> SegNet(i) -> seg[k]
-        #   orb_l, orb_r (the handles' own streams): wait side[k] -> extractor(i)
-        #   side : wait seg[k], orb_l, orb_r -> [all-gather of record k] -> side[k]
-        # so the main stream never waits for an extractor and SegNet(i+1) follows SegNet(i) back to back.
+        # Stream graph of frame i (record k = i mod NBUF):
+        #   main : wait side[k] (frame i-NBUF's record fully consumed) -> SegNet(i) -> wait orb_l, orb_r -> seg[k]
+        #   orb_l, orb_r (the handles' own streams, highest priority): wait side[k] -> extractor(i)
+        #   side : wait seg[k] -> [all-gather of record k] -> side[k]
+        # The extractors start with the frame, i.e. under SegNet's small early launches that leave SMs idle, and the main stream
+        # waits for them before the next frame: measured (profiles/r2_notes.md), letting SegNet run ahead instead (joining the
+        # extractors on the side stream, SIVO_BENCH_JOIN=side) starves their 13 short dependent kernels behind 0.2 ms CTAs.
         if side_used[k]:
             stream.wait_event(ev_side[k])
             if use_async_orb:
@@ -349,6 +353,9 @@ def main():
             orb_l.enqueue_device(d_gl[j].data_ptr(), NET_H, NET_W, NET_W, base + o_kp, base + o_dl, base + 8)
             orb_r.enqueue_device(d_gr[j].data_ptr(), NET_H, NET_W, NET_W, base + o_kr, base + o_dr, base + 16)
             d_rec[k][:8].view(torch.int64).copy_(frame_ids[(rank * 4096 + i) & 0xFFFF:][:1], non_blocking=True)
+            if JOIN_ON_MAIN:
+                orb_l.stream_wait(stream.cuda_stream)
+                orb_r.stream_wait(stream.cuda_stream)
             t2 = t3 = time.perf_counter()
         else:  # host quad tree (nfeatures beyond the device tree's capacity): blocking extractor calls, host-packed record
             fr_ = pool.submit(orb_r.run_device_input, d_gr[j].data_ptr(), NET_H, NET_W, NET_W)
@@ -356,7 +363,7 @@ def main():
             out[1] = fr_.result()
             t2 = time.perf_counter()
             if side_used[k]:
-                ev_seg[k].synchronize()  # the upload that last read this pinned buffer (two frames ago) has been consumed
+                ev_seg[k].synchronize()  # the upload that last read this pinned buffer (NBUF frames ago) has been consumed
             record.pack_host_part(h_rec[k], hw, kp_cap, rank * 100000 + i, out[0][0], out[0][1], out[1][0], out[1][1])
             t3 = time.perf_counter()
             d_rec[k][:record.HEADER].copy_(h_rec_t[k][:record.HEADER], non_blocking=True)
@@ -364,7 +371,7 @@ def main():
         ev_seg[k].record(stream)
         with torch.cuda.stream(side):
             side.wait_event(ev_seg[k])
-            if use_async_orb:
+            if use_async_orb and not JOIN_ON_MAIN:
                 orb_l.stream_wait(side.cuda_stream)
                 orb_r.stream_wait(side.cuda_stream)
             if world > 1:
@@ -376,10 +383,11 @@ def main():
         prof["orb"] += t2 - t1
         prof["pack"] += t3 - t2
         prof["gather"] += t4 - t3
-        if (i & 3) == 3 and side_used[k ^ 1]:
+        kp = (i - 1) % NBUF
+        if (i & 3) == 3 and side_used[kp]:
             # bounded run-ahead: nothing above waits for the GPU, so without this the host would queue the whole run at once.
             # Waiting for the PREVIOUS frame keeps one frame queued behind the one that is running (no bubble)
-            ev_side[k ^ 1].synchronize()
+            ev_side[kp].synchronize()
         return out
 
     # e2e buffers: page-locked host memory, as the contract asks (inputs from pinned memory; the results land in
@@ -422,7 +430,7 @@ def main():
         out = [fl_.result(), fr_.result()]
         if world > 1:
             # N > 1: the frame's record is shared with every rank -- pack the host results, upload, all-gather, wait
-            k = i & 1
+            k = i % NBUF
             record.pack_host(h_rec[k], hw, kp_cap, rank * 100000 + i, res[0], res[1], res[2], out[0][0], out[0][1], out[1][0], out[1][1])
             d_rec[k].copy_(h_rec_t[k], non_blocking=True)
             dist.all_gather_into_tensor(d_all[k], d_rec[k])
@@ -438,7 +446,7 @@ def main():
     # ---- value: inputs resident in HBM
     # set-up, not a step: the library captures one CUDA graph per (input, output, stream) pointer set the caller uses; touch every
     # input buffer of the rotation once so that no capture falls into the timed region whatever --warmup is
-    for i in range(2 * n_frames):
+    for i in range(n_frames * NBUF):  # every (input buffer, record buffer) pair of the rotation: i mod n_frames x i mod NBUF
         device_step(i)
     for i in range(args.warmup):
         device_step(i)
@@ -446,6 +454,9 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    import gc
+    gc.collect()
+    gc.disable()  # a collection pause inside a 20-ms timed region would be a visible fraction of it
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     t0 = time.perf_counter()
@@ -459,21 +470,26 @@ def main():
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
+    gc.enable()
     prof_value = dict(prof)  # the sustained leg and the e2e variants call device_step / the extractors again
     dev_ms = e0.elapsed_time(e1)
     elapsed = max(wall, dev_ms / 1e3)  # the ORB streams are the library's own; wall brackets everything (synced both sides)
     # ---- e2e: host buffers through the operator calls, three call patterns (the first is the headline)
     e2e_times = {}
+    E2E_REPEATS = 3  # each measurement is exactly --steps frames; the median of three damps host-thread scheduling jitter
     for name, order, pinned in (("reference_order_pinned", "reference", True), ("concurrent_pinned", "concurrent", True),
                                 ("reference_order_pageable", "reference", False)):
         for i in range(max(2, args.warmup // 2)):
             host_step(i, order, pinned)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            res, out = host_step(args.warmup + i, order, pinned)
-        barrier()
-        e2e_times[name] = time.perf_counter() - t0
+        reps = []
+        for _ in range(E2E_REPEATS):
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                res, out = host_step(args.warmup + i, order, pinned)
+            barrier()
+            reps.append(time.perf_counter() - t0)
+        e2e_times[name] = float(np.median(reps))
     e2e_elapsed = e2e_times["reference_order_pinned"]
     clocks = sampler.stop() if rank == 0 else None
     n_kp = len(out[0][0]) + len(out[1][0])
@@ -599,9 +615,10 @@ def main():
                         "d2h_bytes_per_step": int(d2h), "calls": "reference order (segmentImage, then the two extractor threads), page-locked buffers"},
                 "e2e_variants": {n: {"value": total_frames / t, "unit": "frames/s", "ms_per_step": 1e3 * t / args.steps} for n, t in e2e_times.items()},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu_base,
-                "host_ms_per_step": {k: round(1e3 * v / (args.steps + args.warmup + 2 * n_frames), 3) for k, v in prof_value.items()},
+                "host_ms_per_step": {k: round(1e3 * v / (args.steps + args.warmup + n_frames * NBUF), 3) for k, v in prof_value.items()},
                 "orb_last_call": {"left": orb_l.last_timing(), "right": orb_r.last_timing()},
-                "host_issue_ms_per_step": {"min": float(step_ms.min()), "median": float(np.median(step_ms)), "max": float(step_ms.max())},
+                "host_issue_ms_per_step": {"min": float(step_ms.min()), "median": float(np.median(step_ms)), "max": float(step_ms.max()),
+                                           "argmax": int(step_ms.argmax()), "all": [round(float(v), 3) for v in step_ms]},
                 "keypoints_last_frame": int(n_kp)}
         print(json.dumps(line))
     if world > 1:

@@ -319,7 +319,7 @@ int sivo_dbg_orb_distribute_device(int device, const int* xs, const int* ys, con
     SIVO_CUDA(cudaMemcpy(d_cand.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
     SIVO_CUDA(cudaMemcpy(d_off.p, off, sizeof off, cudaMemcpyHostToDevice));
     SIVO_CUDA(cudaMemset(d_cnt.p, 0, 2 * sizeof(int)));
-    orb_launch_distribute(d_cand.as<uint32_t>(), d_off.as<int>(), prm, 1, d_sel.as<uint32_t>(), d_cnt.as<int>(), d_cnt.as<int>() + 1, nullptr);
+    orb_launch_distribute(d_cand.as<uint32_t>(), d_off.as<int>(), nullptr, nullptr, prm, 1, d_sel.as<uint32_t>(), d_cnt.as<int>(), d_cnt.as<int>() + 1, nullptr);
     int ce[2] = {0, 0};
     SIVO_CUDA(cudaMemcpy(ce, d_cnt.p, sizeof ce, cudaMemcpyDeviceToHost));
     if (ce[1]) fail(SIVO_ERANGE, "input exceeds the device quad tree's capacity");

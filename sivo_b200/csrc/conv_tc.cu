@@ -53,6 +53,7 @@ struct TcParams {
   int w_rep;               // weight tensor replicas in global memory (spreads the L2 hot spot all CTAs hammer)
   int dbg_noepi;           // timing experiment only: 1 = epilogue does nothing, 2 = TMEM loads only, 3 = no global stores
   int dbg_noshift;         // timing experiment only: ignore the kw shift of the A operand (wrong results)
+  int dbg_noload;          // timing experiment only: halo rows are loaded once per ring slot and then reused (wrong results)
   int b_stages;            // weight ring depth (as many of kMaxBStages as fit in shared memory)
   int out_f32;             // 1: 16-channel float output (logits); 2: n_tile-wide float output (split-operand fp32 mode)
   int split;               // split-operand fp32 mode: A = [hi Cin | lo Cin] half planes of the float input, B K-axis = per real chunk
@@ -1046,6 +1047,7 @@ k_conv_tc_stack16(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int i = 0; i < R + K - 1; ++i, ++u) {
           const int slot = u % kSlots;
           mbar_wait(a_empty + slot, ((u / kSlots) & 1) ^ 1);
+          if (p.dbg_noload && u >= static_cast<uint32_t>(kSlots)) { mbar_arrive(a_full + slot); continue; }
           mbar_expect_tx(a_full + slot, static_cast<uint32_t>((128 + K - 1) * 128));
           tma_load_4d(a_slots + slot * kSlotBytes, &map_a, a_full + slot, 0, x0 - kPad, y0 - kPad + i, img);
         }
@@ -1225,6 +1227,14 @@ void conv_tc_dispatch(const ConvTcPlan& plan, cudaStream_t s, bool configure) {
 
 namespace {
 void conv_tc_use_stack16(ConvTcPlan& plan, int K);  // below
+// Upper bound on the row blocks one CTA walks.  Long-lived CTAs (one wave of 144 CTAs x 8 blocks = 0.19 ms) amortise the
+// prologue best, but while they run no SM frees up, so the extractors' short dependent kernels -- highest stream priority
+// notwithstanding -- each wait for a whole CTA lifetime; SIVO_B200_TC_MAX_PPC trades the two (unit: row blocks of this kernel;
+// the 16-row full-stack blocks count `scale` x as much).
+int tc_max_ppc(int scale = 1) {
+  static const int v = [] { const char* e = std::getenv("SIVO_B200_TC_MAX_PPC"); return e ? std::max(1, atoi(e)) : 24; }();
+  return std::max(1, v / scale);
+}
 // Output rows per accumulator stage.  4 rows share each weight tile (TMEM: 2 stages x rows x n_tile <= 512 columns), but
 // a layer too small to give every SM a 4-row block runs 2-row blocks instead: twice the CTAs, half the work each.
 int tc_rows(int K, bool roll, int n_tile, int columns = 1 << 30, int H = 1 << 20) {
@@ -1339,7 +1349,7 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   // row blocks per CTA: minimise (waves of 148 SMs) x (blocks per CTA + ~1 block of prologue / halo overhead)
   int ppc = 1;
   double best_cost = 1e30;
-  for (int c = 1; c <= std::min(total_pairs, 24); ++c) {
+  for (int c = 1; c <= std::min(total_pairs, tc_max_ppc()); ++c) {
     const long ctas = static_cast<long>(columns) * ceil_div(total_pairs, c);
     const double cost = static_cast<double>((ctas + 147) / 148) * (c + (roll ? (K - 1.0) / rows * 0.5 + 0.5 : 0.3));
     if (cost < best_cost - 1e-9) { best_cost = cost; ppc = c; }
@@ -1362,6 +1372,8 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   p.dbg_noepi = 0;
   if (const char* e = std::getenv("SIVO_B200_TC_NOEPI")) p.dbg_noepi = atoi(e);
   if (const char* e = std::getenv("SIVO_B200_TC_NOSHIFT")) p.dbg_noshift = e[0] == '1';
+  p.dbg_noload = 0;
+  if (const char* e = std::getenv("SIVO_B200_TC_NOLOAD")) p.dbg_noload = e[0] == '1';
   p.pool_out = nullptr; p.pool_mask = nullptr;
   p.has_cls = 0; p.cls_out = nullptr;
   plan->grid = dim3(p.strips * ceil_div(total_pairs, ppc), cout_tiles, in.n);
@@ -1504,7 +1516,7 @@ void conv_tc_use_stack16(ConvTcPlan& plan, int K) {
   const int columns = p.strips * p.N_batch;
   int ppc = 1;
   double best_cost = 1e30;
-  for (int c = 1; c <= std::min(total_blocks, 24); ++c) {  // (waves of 148 SMs) x (blocks per CTA + weight load / prologue)
+  for (int c = 1; c <= std::min(total_blocks, tc_max_ppc(2)); ++c) {  // (waves of 148 SMs) x (blocks per CTA + weight load / prologue)
     const long ctas = static_cast<long>(columns) * ceil_div(total_blocks, c);
     const double cost = static_cast<double>((ctas + 147) / 148) * (c + 0.35);
     if (cost < best_cost - 1e-9) { best_cost = cost; ppc = c; }

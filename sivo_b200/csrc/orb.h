@@ -3,6 +3,7 @@
 // concurrently from two threads as Frame.cc:126-129 does.
 #pragma once
 #include <condition_variable>
+#include <cstdlib>
 #include <functional>
 #include <memory>
 #include <mutex>
@@ -49,6 +50,7 @@ struct OrbTreeParams {
   float hx[kOrbMaxLevels];      // width / n_ini
   float scale[kOrbMaxLevels];   // mvScaleFactor
   float size[kOrbMaxLevels];    // float(int(PATCH_SIZE * mvScaleFactor[level]))
+  int cell_begin[kOrbMaxLevels], cell_end[kOrbMaxLevels];  // the level's FAST cells in the global cell list
   int min_b;                    // EDGE_THRESHOLD - 3: level coordinate of candidate (0, 0)
 };
 
@@ -58,14 +60,38 @@ struct OrbSelected {  // one retained keypoint, level coordinates
   short pad;
 };
 
+// Programmatic dependent launch for the extractor's chain of short dependent kernels: every kernel starts with
+// `griddepcontrol.launch_dependents; griddepcontrol.wait;` (ORB_PDL_PROLOGUE), so the next grid of the stream is scheduled while
+// this one drains and only its launch latency -- not its work -- overlaps (the wait returns once the previous grid has completed
+// and flushed).  Opt-in (SIVO_B200_ORB_PDL=1; without the attribute the prologue is a no-op): measured on B200 it does not
+// shorten a lone extractor call (0.336 vs 0.312 ms for the concurrent pair) and costs the full frame 10 % (0.855 vs 0.75 ms) --
+// the early CTAs of the next small kernel sit on SMs the convolution CTAs need (profiles/r2_notes.md).
+#define ORB_PDL_PROLOGUE() asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory")
+template <class... KArgs, class... Args>
+inline void orb_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  static const bool pdl = [] { const char* e = std::getenv("SIVO_B200_ORB_PDL"); return e && e[0] == '1'; }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  SIVO_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
+}
+
 // ---- kernels (orb_kernels.cu)
 void orb_launch_pyramid(const uint8_t* gray, int rows, int cols, size_t gray_pitch, uint8_t* pyr, const OrbLevelTable& t,
                         cudaStream_t s);
 void hamming_best2(int device, const uint8_t* query, int nq, const uint8_t* train, int nt, const int* cand_off, const int* cand_idx,
                    const int* train_level, int* out5);
 void orb_launch_score(const uint8_t* pyr, uint8_t* score, const OrbLevelTable& t, int t_min, cudaStream_t s);
-void orb_launch_cells(const uint8_t* score, const OrbLevelTable& t, const OrbCell* cells, int ncells, int ini_th, int min_th,
-                      int* cell_count, uint32_t* cell_items, cudaStream_t s);
+// score == nullptr: the cells score their own pixels from `pyr` (no score-map pass)
+void orb_launch_cells(const uint8_t* score, const uint8_t* pyr, const OrbLevelTable& t, const OrbCell* cells, int ncells, int ini_th,
+                      int min_th, int* cell_count, uint32_t* cell_items, cudaStream_t s);
 void orb_launch_compact(const OrbLevelTable& t, const OrbCell* cells, int ncells, const int* cell_count,
                         const uint32_t* cell_items, int* cell_offset, int* level_offsets, uint32_t* cand, int cand_cap,
                         cudaStream_t s);
@@ -73,13 +99,15 @@ void orb_launch_blur(const uint8_t* pyr, uint8_t* blur, const OrbLevelTable& t, 
 void orb_launch_describe(const uint8_t* pyr, const uint8_t* blur, const OrbLevelTable& t, const OrbSelected* sel, int n,
                          const int* umax, float* angles, uint8_t* desc, cudaStream_t s);
 // the same for a keypoint count that lives on the device (<= cap): angles go straight into the keypoint records
-void orb_launch_describe_dev(const uint8_t* pyr, const uint8_t* blur, const OrbLevelTable& t, const OrbSelected* sel, const int* n_dev,
-                             int cap, const int* umax, sivo_keypoint* kps, uint8_t* desc, cudaStream_t s);
+// Device-tree form: per-level selections (sel_packed[l * kTreeSelCap + i], level_count[l]) -> level-major keypoint records
+// (ComputeKeyPointsOctTree :824-835 + the final scaling of operator() :1071-1078, angle from IC_Angle) and descriptors;
+// *n_out (and *n_out_i64 if given) = the keypoint count, bit 30 of *error if it exceeds cap.
+void orb_launch_describe_dev(const uint8_t* pyr, const uint8_t* blur, const OrbLevelTable& t, const uint32_t* sel_packed,
+                             const int* level_count, const OrbTreeParams& prm, int cap, const int* umax, sivo_keypoint* kps,
+                             uint8_t* desc, int* n_out, long long* n_out_i64, int* error, cudaStream_t s);
 // DistributeOctTree on the device, one block per level (orb_tree.cu), then the level-major keypoint records
-void orb_launch_distribute(const uint32_t* cand, const int* level_off, const OrbTreeParams& prm, int nlevels, uint32_t* sel_packed,
-                           int* level_count, int* error, cudaStream_t s);
-void orb_launch_finalize(const uint32_t* sel_packed, const int* level_count, const OrbTreeParams& prm, int nlevels, int cap,
-                         OrbSelected* sel, sivo_keypoint* kps, int* n_out, long long* n_out_i64, int* error, cudaStream_t s);
+void orb_launch_distribute(const uint32_t* cand, const int* level_off, const uint32_t* cell_items, const int* cell_count,
+                           const OrbTreeParams& prm, int nlevels, uint32_t* sel_packed, int* level_count, int* error, cudaStream_t s);
 void orb_tree_configure();  // raises k_distribute's dynamic shared-memory limit on the current device
 void orb_upload_pattern();  // copies the rBRIEF pair table into constant memory (once per device)
 
@@ -129,12 +157,15 @@ class Orb {
  private:
   void ensure(int rows, int cols);
   void enqueue_front(const uint8_t* src, size_t src_pitch, cudaStream_t s);
+  void enqueue_compact(cudaStream_t s);
+  bool compacted_ = false;
   void enqueue_tree_and_describe(sivo_keypoint* kps_dev, uint8_t* desc_dev, long long* count_dev, cudaStream_t s);
   bool device_tree_ = true;
   OrbTreeParams tree_prm_{};
   DevBuf d_sel_packed_, d_level_count_, d_n_err_, d_kps_;
   PinnedBuf h_n_err_, h_kps_;
-  cudaEvent_t ev_wait_ = nullptr, ev_wait2_ = nullptr;
+  cudaEvent_t ev_wait_ = nullptr, ev_wait2_ = nullptr, ev_pyr_ = nullptr;
+  cudaStream_t copy_stream_ = nullptr;
   int nfeatures_, nlevels_, ini_th_, min_th_, device_;
   float scale_factor_;
   OrbTables tab_;

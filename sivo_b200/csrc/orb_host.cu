@@ -331,6 +331,7 @@ Orb::Orb(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th,
       h_n_err_.ensure(2 * sizeof(int));
       h_kps_.ensure(static_cast<size_t>(sel_cap_) * sizeof(sivo_keypoint));
       SIVO_CUDA(cudaEventCreateWithFlags(&ev_wait_, cudaEventDisableTiming));
+      SIVO_CUDA(cudaEventCreateWithFlags(&ev_pyr_, cudaEventDisableTiming));
     }
   }
   d_level_off_.alloc((kOrbMaxLevels + 1) * sizeof(int));
@@ -341,6 +342,8 @@ Orb::~Orb() {
   cudaSetDevice(device_);
   for (auto& e : ev_) if (e) cudaEventDestroy(e);
   if (ev_wait_) cudaEventDestroy(ev_wait_);
+  if (ev_pyr_) cudaEventDestroy(ev_pyr_);
+  if (copy_stream_) cudaStreamDestroy(copy_stream_);
   if (ev_wait2_) cudaEventDestroy(ev_wait2_);
   if (stream_) cudaStreamDestroy(stream_);
 }
@@ -411,6 +414,7 @@ void Orb::ensure(int rows, int cols) {
   }
   pyr_bytes_ = img_off;
   flat_bytes_ = flat_off;
+  for (int l = 0; l < nlevels_; ++l) { tree_prm_.cell_begin[l] = lt_.lv[l].cell_begin; tree_prm_.cell_end[l] = lt_.lv[l].cell_end; }
   const int ncells = static_cast<int>(cells_.size());
   d_gray_.alloc(static_cast<size_t>(rows) * cols);
   h_gray_.ensure(static_cast<size_t>(rows) * cols);
@@ -460,7 +464,7 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
   bool pyr_direct = pyr_out != nullptr;
   if (pyr_out)
     for (int l = 0; l < nlevels_; ++l) pyr_direct = pyr_direct && pyr_out[l] && is_pinned_host(pyr_out[l]);
-  auto enqueue_pyramid_readback = [&] {
+  auto enqueue_pyramid_readback = [&](cudaStream_t s) {
     if (pyr_out && pyr_direct) {  // page-locked level buffers (mvImagePyramid storage): strided copies straight into them
       for (int l = 0; l < nlevels_; ++l) {
         const OrbLevel& lv = lt_.lv[l];
@@ -487,7 +491,16 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
   };
   bool pyramid_enqueued = false;
   if (device_tree_) {
-    // ---- device quad tree: one asynchronous chain, one synchronisation at the end
+    // ---- device quad tree: one asynchronous chain, one synchronisation at the end; the 1.6 MB pyramid read-back (the public
+    // mvImagePyramid) leaves on a second stream as soon as the level images exist, under FAST / tree / describe
+    if (pyr_out) {
+      if (!copy_stream_) {
+        SIVO_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+      }
+      SIVO_CUDA(cudaStreamWaitEvent(copy_stream_, ev_pyr_, 0));
+      enqueue_pyramid_readback(copy_stream_);
+      pyramid_enqueued = true;
+    }
     SIVO_CUDA(cudaEventRecord(ev_[1], s));
     enqueue_tree_and_describe(d_kps_.as<sivo_keypoint>(), d_desc_.as<uint8_t>(), nullptr, s);
     SIVO_CUDA(cudaEventRecord(ev_[2], s));
@@ -495,10 +508,9 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
     SIVO_CUDA(cudaMemcpyAsync(h_kps_.p, d_kps_.p, static_cast<size_t>(sel_cap_) * sizeof(sivo_keypoint), cudaMemcpyDeviceToHost, s));
     SIVO_CUDA(cudaMemcpyAsync(h_desc_.p, d_desc_.p, static_cast<size_t>(sel_cap_) * 32, cudaMemcpyDeviceToHost, s));
     SIVO_CUDA(cudaEventRecord(ev_[3], s));
-    enqueue_pyramid_readback();
-    pyramid_enqueued = true;
-    launches = nlevels_ + 8;
+    launches = nlevels_ + 4;
     SIVO_CUDA(cudaStreamSynchronize(s));
+    if (pyramid_enqueued) SIVO_CUDA(cudaStreamSynchronize(copy_stream_));
     const int total = h_n_err_.as<int>()[0], err = h_n_err_.as<int>()[1];
     if (!err) {
       float a = 0, b2 = 0;
@@ -516,13 +528,14 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
     }
     // a level exceeded the device tree's caps: take the host path below (the candidates are still on the device)
   }
+  enqueue_compact(s);
   SIVO_CUDA(cudaMemcpyAsync(h_level_off_.p, d_level_off_.p, (nlevels_ + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
   SIVO_CUDA(cudaMemcpyAsync(h_cand_.p, d_cand_.p, static_cast<size_t>(cand_cap_) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   SIVO_CUDA(cudaEventRecord(ev_[1], s));
   // the blur and the pyramid read-back overlap the host quad tree
   orb_launch_blur(d_pyr_.as<uint8_t>(), d_blur_.as<uint8_t>(), lt_, s);
-  if (!pyramid_enqueued) enqueue_pyramid_readback();
-  launches = nlevels_ + 5;
+  if (!pyramid_enqueued) enqueue_pyramid_readback(s);
+  launches = nlevels_ + 6;
   static const bool trace = [] { const char* e = std::getenv("SIVO_B200_ORB_TRACE"); return e && e[0] == '1'; }();
   const auto w1 = std::chrono::steady_clock::now();
   SIVO_CUDA(cudaEventSynchronize(ev_[1]));
@@ -632,29 +645,36 @@ void Orb::run(const uint8_t* gray, int rows, int cols, size_t stride, sivo_keypo
     if (kps) kps[i] = kp;
   }
   if (desc && total) memcpy(desc, h_desc_.p, static_cast<size_t>(total) * 32);
+  if (pyramid_enqueued && copy_stream_) SIVO_CUDA(cudaStreamSynchronize(copy_stream_));
   copy_out_pyramid();
 }
 
 void Orb::enqueue_front(const uint8_t* src, size_t src_pitch, cudaStream_t s) {
   const int ncells = static_cast<int>(cells_.size());
   orb_launch_pyramid(src, rows_, cols_, src_pitch, d_pyr_.as<uint8_t>(), lt_, s);
-  orb_launch_score(d_pyr_.as<uint8_t>(), d_score_.as<uint8_t>(), lt_, std::min(ini_th_, min_th_), s);
-  orb_launch_cells(d_score_.as<uint8_t>(), lt_, d_cells_.as<OrbCell>(), ncells, ini_th_, min_th_, d_cell_count_.as<int>(),
-                   d_cell_items_.as<uint32_t>(), s);
-  orb_launch_compact(lt_, d_cells_.as<OrbCell>(), ncells, d_cell_count_.as<int>(), d_cell_items_.as<uint32_t>(),
+  if (ev_pyr_) SIVO_CUDA(cudaEventRecord(ev_pyr_, s));  // the level images are final: their read-back can start on the copy stream
+  static const bool fused_score = [] { const char* e = std::getenv("SIVO_B200_ORB_FUSED_SCORE"); return !(e && e[0] == '0'); }();
+  if (!fused_score) orb_launch_score(d_pyr_.as<uint8_t>(), d_score_.as<uint8_t>(), lt_, std::min(ini_th_, min_th_), s);
+  orb_launch_cells(fused_score ? nullptr : d_score_.as<uint8_t>(), d_pyr_.as<uint8_t>(), lt_, d_cells_.as<OrbCell>(), ncells, ini_th_, min_th_,
+                   d_cell_count_.as<int>(), d_cell_items_.as<uint32_t>(), s);
+  compacted_ = false;  // the device tree reads the cell lists directly; the host path and the test hook compact on demand
+}
+
+void Orb::enqueue_compact(cudaStream_t s) {
+  if (compacted_) return;
+  orb_launch_compact(lt_, d_cells_.as<OrbCell>(), static_cast<int>(cells_.size()), d_cell_count_.as<int>(), d_cell_items_.as<uint32_t>(),
                      d_cell_offset_.as<int>(), d_level_off_.as<int>(), d_cand_.as<uint32_t>(), cand_cap_, s);
+  compacted_ = true;
 }
 
 void Orb::enqueue_tree_and_describe(sivo_keypoint* kps_dev, uint8_t* desc_dev, long long* count_dev, cudaStream_t s) {
   int* n_dev = d_n_err_.as<int>();
   SIVO_CUDA(cudaMemsetAsync(n_dev, 0, 2 * sizeof(int), s));
-  orb_launch_distribute(d_cand_.as<uint32_t>(), d_level_off_.as<int>(), tree_prm_, nlevels_, d_sel_packed_.as<uint32_t>(),
-                        d_level_count_.as<int>(), n_dev + 1, s);
-  orb_launch_finalize(d_sel_packed_.as<uint32_t>(), d_level_count_.as<int>(), tree_prm_, nlevels_, sel_cap_, d_sel_.as<OrbSelected>(),
-                      kps_dev, n_dev, count_dev, n_dev + 1, s);
   orb_launch_blur(d_pyr_.as<uint8_t>(), d_blur_.as<uint8_t>(), lt_, s);
-  orb_launch_describe_dev(d_pyr_.as<uint8_t>(), d_blur_.as<uint8_t>(), lt_, d_sel_.as<OrbSelected>(), n_dev, sel_cap_,
-                          d_umax_.as<int>(), kps_dev, desc_dev, s);
+  orb_launch_distribute(nullptr, nullptr, d_cell_items_.as<uint32_t>(), d_cell_count_.as<int>(), tree_prm_, nlevels_,
+                        d_sel_packed_.as<uint32_t>(), d_level_count_.as<int>(), n_dev + 1, s);
+  orb_launch_describe_dev(d_pyr_.as<uint8_t>(), d_blur_.as<uint8_t>(), lt_, d_sel_packed_.as<uint32_t>(), d_level_count_.as<int>(), tree_prm_,
+                          sel_cap_, d_umax_.as<int>(), kps_dev, desc_dev, n_dev, count_dev, n_dev + 1, s);
 }
 
 void Orb::enqueue_device(const uint8_t* gray_dev, int rows, int cols, size_t pitch, sivo_keypoint* kps_dev, uint8_t* desc_dev,
@@ -666,7 +686,7 @@ void Orb::enqueue_device(const uint8_t* gray_dev, int rows, int cols, size_t pit
   ensure(rows, cols);
   enqueue_front(gray_dev, pitch, stream_);
   enqueue_tree_and_describe(kps_dev, desc_dev, count_dev, stream_);
-  launches = nlevels_ + 8;
+  launches = nlevels_ + 4;
   last_off_.clear();
 }
 
@@ -701,6 +721,7 @@ int Orb::device_tree_status() {
 void Orb::candidates(int level, int* xs, int* ys, int* resp, int cap, int* n) const {
   if (last_off_.empty() && rows_ > 0) {  // device-tree runs leave the candidates on the device: fetch them on demand
     SIVO_CUDA(cudaSetDevice(device_));
+    const_cast<Orb*>(this)->enqueue_compact(stream_);
     last_off_.resize(nlevels_ + 1);
     SIVO_CUDA(cudaMemcpyAsync(last_off_.data(), d_level_off_.p, (nlevels_ + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream_));
     SIVO_CUDA(cudaStreamSynchronize(stream_));

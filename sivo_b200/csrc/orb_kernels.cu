@@ -22,6 +22,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 
 // ---- level 0: copyMakeBorder(image, 19, BORDER_REFLECT_101) (ORBextractor.cc:1112-1119)
 __global__ void k_level0(const uint8_t* __restrict__ gray, size_t gpitch, uint8_t* __restrict__ dst, OrbLevel lv) {
+  ORB_PDL_PROLOGUE();
   int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
   if (bx >= lv.w + 2 * kEdge) return;
   int x = reflect101(bx - kEdge, lv.w), y = reflect101(by - kEdge, lv.h);
@@ -47,6 +48,7 @@ __device__ __forceinline__ Coef lin_coef(int d, int dn, int sn) {
 }
 
 __global__ void k_resize(uint8_t* __restrict__ pyr, OrbLevel src, OrbLevel dst) {
+  ORB_PDL_PROLOGUE();
   int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
   if (bx >= dst.w + 2 * kEdge) return;
   int dx = reflect101(bx - kEdge, dst.w), dy = reflect101(by - kEdge, dst.h);
@@ -66,49 +68,46 @@ __global__ void k_resize(uint8_t* __restrict__ pyr, OrbLevel src, OrbLevel dst) 
 // `t_min` = the smallest threshold any consumer applies (min(iniThFAST, minThFAST)): a 9-arc covers at least two of the four
 // compass points, so a pixel with fewer than two compass points brighter than p + t_min and fewer than two darker than
 // p - t_min has S < t_min, is zeroed by every threshold, and gets 0 without the full score (most pixels).
+__device__ __forceinline__ int fast_score_at(const uint8_t* __restrict__ pyr, const OrbLevel& lv, int x, int y, int t_min) {
+  if (!(x >= kEdge && x < lv.w - kEdge && y >= kEdge && y < lv.h - kEdge)) return 0;
+  const uint8_t* c = pyr + lv.img_off + static_cast<size_t>(y + kEdge) * lv.pitch + x + kEdge;
+  const int P = lv.pitch;
+  const int off[16] = {3 * P,      3 * P + 1,  2 * P + 2,  P + 3,  3,  -P + 3,  -2 * P + 2, -3 * P + 1,
+                       -3 * P,     -3 * P - 1, -2 * P - 2, -P - 3, -3, P - 3,   2 * P - 2,  3 * P - 1};
+  const int v = c[0];
+  {
+    const int q[4] = {static_cast<int>(c[3 * P]) - v, static_cast<int>(c[3]) - v, static_cast<int>(c[-3 * P]) - v, static_cast<int>(c[-3]) - v};
+    int nb = 0, nd = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { nb += q[k] > t_min; nd += q[k] < -t_min; }
+    if (nb < 2 && nd < 2) return 0;
+  }
+  int d[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) d[k] = static_cast<int>(c[off[k]]) - v;
+  int best = -255;
+#pragma unroll
+  for (int sgn = 0; sgn < 2; ++sgn) {
+    int m2[16], m4[16], m8[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m2[k] = min(d[k], d[(k + 1) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m4[k] = min(m2[k], m2[(k + 2) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m8[k] = min(m4[k], m4[(k + 4) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) best = max(best, min(m8[k], d[(k + 8) & 15]));
+#pragma unroll
+    for (int k = 0; k < 16; ++k) d[k] = -d[k];
+  }
+  return max(best - 1, 0);
+}
+
 __global__ void k_fast_score(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score, OrbLevelTable t, int t_min) {
   const OrbLevel lv = t.lv[blockIdx.y];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= lv.w * lv.h) return;
-  int x = i % lv.w, y = i / lv.w;
-  uint8_t out = 0;
-  if (x >= kEdge && x < lv.w - kEdge && y >= kEdge && y < lv.h - kEdge) {
-    const uint8_t* c = pyr + lv.img_off + static_cast<size_t>(y + kEdge) * lv.pitch + x + kEdge;
-    const int P = lv.pitch;
-    const int off[16] = {3 * P,      3 * P + 1,  2 * P + 2,  P + 3,  3,  -P + 3,  -2 * P + 2, -3 * P + 1,
-                         -3 * P,     -3 * P - 1, -2 * P - 2, -P - 3, -3, P - 3,   2 * P - 2,  3 * P - 1};
-    int v = c[0];
-    {
-      const int q[4] = {static_cast<int>(c[3 * P]) - v, static_cast<int>(c[3]) - v, static_cast<int>(c[-3 * P]) - v, static_cast<int>(c[-3]) - v};
-      int nb = 0, nd = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { nb += q[k] > t_min; nd += q[k] < -t_min; }
-      if (nb < 2 && nd < 2) {
-        score[lv.flat_off + i] = 0;
-        return;
-      }
-    }
-    int d[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) d[k] = static_cast<int>(c[off[k]]) - v;
-    int best = -255;
-#pragma unroll
-    for (int sgn = 0; sgn < 2; ++sgn) {
-      int m2[16], m4[16], m8[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) m2[k] = min(d[k], d[(k + 1) & 15]);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) m4[k] = min(m2[k], m2[(k + 2) & 15]);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) m8[k] = min(m4[k], m4[(k + 4) & 15]);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) best = max(best, min(m8[k], d[(k + 8) & 15]));
-#pragma unroll
-      for (int k = 0; k < 16; ++k) d[k] = -d[k];
-    }
-    out = static_cast<uint8_t>(max(best - 1, 0));
-  }
-  score[lv.flat_off + i] = out;
+  score[lv.flat_off + i] = static_cast<uint8_t>(fast_score_at(pyr, lv, i % lv.w, i / lv.w, t_min));
 }
 
 // ---- one block per 30-px cell: cv::FAST(cell, iniThFAST, NMS) with the minThFAST retry when the cell
@@ -133,9 +132,12 @@ __device__ int block_exclusive_scan(int flag, int* s_warp, int& total) {
   return base + within;
 }
 
-__global__ void __launch_bounds__(kCellThreads) k_cells(const uint8_t* __restrict__ score, OrbLevelTable t,
+// score == nullptr: the cell computes its own FAST scores from the pyramid (cell interiors tile the level without overlap, so
+// this is the same work as the score-map kernel minus one launch and the 1.1 MB map written and read back)
+__global__ void __launch_bounds__(kCellThreads) k_cells(const uint8_t* __restrict__ score, const uint8_t* __restrict__ pyr, OrbLevelTable t,
                                                         const OrbCell* __restrict__ cells, int ini_th, int min_th,
                                                         int* __restrict__ cell_count, uint32_t* __restrict__ cell_items) {
+  ORB_PDL_PROLOGUE();
   __shared__ uint8_t s[(kCellMaxDim + 2) * (kCellMaxDim + 2)];
   __shared__ int s_warp[kCellThreads / 32];
   __shared__ int s_any;
@@ -152,7 +154,9 @@ __global__ void __launch_bounds__(kCellThreads) k_cells(const uint8_t* __restric
   for (int e = threadIdx.x; e < (ih + 2) * sw; e += kCellThreads) {
     int x = e % sw - 1, y = e / sw - 1;
     uint8_t v = 0;
-    if (x >= 0 && x < iw && y >= 0 && y < ih) v = sc[static_cast<size_t>(iy0 + y) * lv.w + ix0 + x];
+    if (x >= 0 && x < iw && y >= 0 && y < ih)
+      v = score ? sc[static_cast<size_t>(iy0 + y) * lv.w + ix0 + x]
+                : static_cast<uint8_t>(fast_score_at(pyr, lv, ix0 + x, iy0 + y, min(ini_th, min_th)));
     s[e] = v;  // outside the sub-image's 3-px apron the score is 0 by construction of cv::FAST
   }
   if (threadIdx.x == 0) s_any = 0;
@@ -211,19 +215,39 @@ __global__ void __launch_bounds__(kCellThreads) k_cells(const uint8_t* __restric
 // ---- cell lists -> one candidate array in the reference's vToDistributeKeys order (level, cell row, cell col)
 __global__ void k_scan_cells(OrbLevelTable t, int ncells, const int* __restrict__ cell_count, int* __restrict__ cell_offset,
                              int* __restrict__ level_offsets) {
-  // single block; ncells <= ~1200
-  __shared__ int s[2048];
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x) s[i] = i < ncells ? cell_count[i] : 0;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int i = 0; i < ncells; ++i) { int c = s[i]; s[i] = run; run += c; }
-    s[ncells] = run;
+  // single block of 256 threads, ncells < 2048: eight consecutive cells per thread, warp + block scan of the partial sums
+  __shared__ int s[2049];
+  __shared__ int wsum[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int v[8], sum = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = tid * 8 + k;
+    v[k] = i < ncells ? cell_count[i] : 0;
+    sum += v[k];
   }
+  int inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int x = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += x;
+  }
+  if (lane == 31) wsum[warp] = inc;
   __syncthreads();
-  for (int i = threadIdx.x; i <= ncells; i += blockDim.x) cell_offset[i] = s[i];
-  if (threadIdx.x <= t.nlevels) {
-    int l = threadIdx.x;
+  int base = 0;
+  for (int w = 0; w < warp; ++w) base += wsum[w];
+  int run = base + inc - sum;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = tid * 8 + k;
+    if (i <= 2048) s[i] = run;
+    run += v[k];
+  }
+  if (tid == 255) s[2048] = run;
+  __syncthreads();
+  for (int i = tid; i <= ncells; i += blockDim.x) cell_offset[i] = s[i];
+  if (tid <= t.nlevels) {
+    const int l = tid;
     level_offsets[l] = l < t.nlevels ? s[t.lv[l].cell_begin] : s[ncells];
   }
 }
@@ -241,6 +265,7 @@ __global__ void k_gather_cells(const int* __restrict__ cell_count, const int* __
 // blurs (`mvImagePyramid[level].clone()`, ORBextractor.cc:1060-1062).
 // One thread = four horizontally adjacent pixels: 10 bytes per source row serve four 7-tap row sums.
 __global__ void k_blur(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, OrbLevelTable t) {
+  ORB_PDL_PROLOGUE();
   const OrbLevel lv = t.lv[blockIdx.y];
   const int wq = (lv.w + 3) >> 2;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -292,15 +317,41 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 // ---- one warp per keypoint: IC_Angle (ORBextractor.cc:75-100) then computeOrbDescriptor (:104-150).
-// n_dev != nullptr: the keypoint count lives on the device (device quad tree) and the angle goes into the keypoint record
+// Device-tree form (sel_packed != nullptr): the per-level selections of k_distribute are concatenated level-major on the fly --
+// every warp derives the level offsets from the eight counts -- and the finished keypoint record is written here
+// (ComputeKeyPointsOctTree :824-835, operator() :1071-1078), so no separate pass builds the OrbSelected list.
 __global__ void k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, OrbLevelTable t,
                            const OrbSelected* __restrict__ sel, int n, const int* __restrict__ umax,
-                           float* __restrict__ angles, uint8_t* __restrict__ desc, const int* __restrict__ n_dev,
-                           sivo_keypoint* __restrict__ kps) {
+                           float* __restrict__ angles, uint8_t* __restrict__ desc, const uint32_t* __restrict__ sel_packed,
+                           const int* __restrict__ level_count, OrbTreeParams prm, sivo_keypoint* __restrict__ kps,
+                           int* __restrict__ n_out, long long* __restrict__ n_out_i64, int* __restrict__ out_error) {
+  ORB_PDL_PROLOGUE();
   int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (n_dev) n = min(n, *n_dev);
-  if (wid >= n) return;
-  const OrbSelected kp = sel[wid];
+  OrbSelected kp;
+  uint32_t packed = 0;
+  if (sel_packed) {
+    int off = 0, lvl = -1, idx = 0;
+    for (int l = 0; l < t.nlevels; ++l) {
+      const int c = level_count[l];
+      if (lvl < 0 && wid < off + c) { lvl = l; idx = wid - off; }
+      off += c;
+    }
+    const bool too_many = off > n;  // n = capacity of the output buffers
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      if (too_many) atomicOr(out_error, 1 << 30);
+      *n_out = too_many ? 0 : off;
+      if (n_out_i64) *n_out_i64 = too_many ? 0 : off;
+    }
+    if (too_many || lvl < 0) return;
+    packed = sel_packed[lvl * kTreeSelCap + idx];
+    kp.x = static_cast<short>(static_cast<int>(packed & 0xFFF) + prm.min_b);
+    kp.y = static_cast<short>(static_cast<int>((packed >> 12) & 0xFFF) + prm.min_b);
+    kp.level = static_cast<short>(lvl);
+    kp.pad = 0;
+  } else {
+    if (wid >= n) return;
+    kp = sel[wid];
+  }
   const OrbLevel lv = t.lv[kp.level];
   // intensity centroid over the radius-15 disc: lane = row v + 15
   int m10 = 0, m01 = 0;
@@ -322,7 +373,22 @@ __global__ void k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __res
     m01 += __shfl_xor_sync(0xffffffffu, m01, o);
   }
   const float angle = fast_atan2_deg(static_cast<float>(m01), static_cast<float>(m10));
-  if (lane == 0) { if (kps) kps[wid].angle = angle; else angles[wid] = angle; }
+  if (lane == 0) {
+    if (sel_packed) {
+      sivo_keypoint o;
+      o.x = static_cast<float>(kp.x);
+      o.y = static_cast<float>(kp.y);
+      if (kp.level != 0) { o.x = __fmul_rn(o.x, prm.scale[kp.level]); o.y = __fmul_rn(o.y, prm.scale[kp.level]); }
+      o.size = prm.size[kp.level];
+      o.angle = angle;
+      o.response = static_cast<float>(packed >> 24);
+      o.octave = kp.level;
+      o.class_id = -1;
+      kps[wid] = o;
+    } else {
+      angles[wid] = angle;
+    }
+  }
   // rotated BRIEF: lane = descriptor byte
   const float factor_pi = static_cast<float>(3.141592653589793238462643383279502884 / 180.f);
   const float ang = __fmul_rn(angle, factor_pi);
@@ -358,8 +424,8 @@ void orb_launch_pyramid(const uint8_t* gray, int rows, int cols, size_t gray_pit
   for (int l = 0; l < t.nlevels; ++l) {
     const OrbLevel& lv = t.lv[l];
     dim3 grid(ceil_div(lv.w + 2 * kEdge, 128), lv.h + 2 * kEdge);
-    if (l == 0) k_level0<<<grid, 128, 0, s>>>(gray, gray_pitch, pyr, lv);
-    else k_resize<<<grid, 128, 0, s>>>(pyr, t.lv[l - 1], lv);
+    if (l == 0) orb_launch_pdl(k_level0, grid, dim3(128), 0, s, gray, gray_pitch, pyr, lv);
+    else orb_launch_pdl(k_resize, grid, dim3(128), 0, s, pyr, t.lv[l - 1], lv);
   }
   SIVO_CUDA(cudaGetLastError());
 }
@@ -370,10 +436,10 @@ void orb_launch_score(const uint8_t* pyr, uint8_t* score, const OrbLevelTable& t
   SIVO_CUDA(cudaGetLastError());
 }
 
-void orb_launch_cells(const uint8_t* score, const OrbLevelTable& t, const OrbCell* cells, int ncells, int ini_th, int min_th,
-                      int* cell_count, uint32_t* cell_items, cudaStream_t s) {
+void orb_launch_cells(const uint8_t* score, const uint8_t* pyr, const OrbLevelTable& t, const OrbCell* cells, int ncells, int ini_th,
+                      int min_th, int* cell_count, uint32_t* cell_items, cudaStream_t s) {
   if (ncells == 0) return;
-  k_cells<<<ncells, kCellThreads, 0, s>>>(score, t, cells, ini_th, min_th, cell_count, cell_items);
+  orb_launch_pdl(k_cells, dim3(ncells), dim3(kCellThreads), 0, s, score, pyr, t, cells, ini_th, min_th, cell_count, cell_items);
   SIVO_CUDA(cudaGetLastError());
 }
 
@@ -389,21 +455,23 @@ void orb_launch_compact(const OrbLevelTable& t, const OrbCell* cells, int ncells
 
 void orb_launch_blur(const uint8_t* pyr, uint8_t* blur, const OrbLevelTable& t, cudaStream_t s) {
   dim3 grid(ceil_div(((t.lv[0].w + 3) / 4) * t.lv[0].h, 128), t.nlevels);
-  k_blur<<<grid, 128, 0, s>>>(pyr, blur, t);
+  orb_launch_pdl(k_blur, grid, dim3(128), 0, s, pyr, blur, t);
   SIVO_CUDA(cudaGetLastError());
 }
 
 void orb_launch_describe(const uint8_t* pyr, const uint8_t* blur, const OrbLevelTable& t, const OrbSelected* sel, int n,
                          const int* umax, float* angles, uint8_t* desc, cudaStream_t s) {
   if (n == 0) return;
-  k_describe<<<ceil_div(n * 32, 128), 128, 0, s>>>(pyr, blur, t, sel, n, umax, angles, desc, nullptr, nullptr);
+  k_describe<<<ceil_div(n * 32, 128), 128, 0, s>>>(pyr, blur, t, sel, n, umax, angles, desc, nullptr, nullptr, OrbTreeParams{}, nullptr, nullptr, nullptr, nullptr);
   SIVO_CUDA(cudaGetLastError());
 }
 
-void orb_launch_describe_dev(const uint8_t* pyr, const uint8_t* blur, const OrbLevelTable& t, const OrbSelected* sel, const int* n_dev,
-                             int cap, const int* umax, sivo_keypoint* kps, uint8_t* desc, cudaStream_t s) {
+void orb_launch_describe_dev(const uint8_t* pyr, const uint8_t* blur, const OrbLevelTable& t, const uint32_t* sel_packed,
+                             const int* level_count, const OrbTreeParams& prm, int cap, const int* umax, sivo_keypoint* kps,
+                             uint8_t* desc, int* n_out, long long* n_out_i64, int* error, cudaStream_t s) {
   if (cap == 0) return;
-  k_describe<<<ceil_div(cap * 32, 128), 128, 0, s>>>(pyr, blur, t, sel, cap, umax, nullptr, desc, n_dev, kps);
+  orb_launch_pdl(k_describe, dim3(ceil_div(cap * 32, 128)), dim3(128), 0, s, pyr, blur, t, static_cast<const OrbSelected*>(nullptr), cap, umax,
+                 static_cast<float*>(nullptr), desc, sel_packed, level_count, prm, kps, n_out, n_out_i64, error);
   SIVO_CUDA(cudaGetLastError());
 }
 

@@ -43,7 +43,6 @@ struct TreeSmem {
   unsigned int sortkey[kTreeListCap];
   int scan[kTreeWarps];
   int warp_cnt[kTreeWarps][16];
-  unsigned short c4[4];
   int n_nodes, size, base_len, n_front, n_pend, n_pend2, seq, error, finish;
 };
 
@@ -76,9 +75,10 @@ __device__ int block_exscan(int v, int* scratch, int* total) {
   return warp_off + inc - v;
 }
 
-// One warp splits node `id` (ExtractorNode::DivideNode): stable 4-way partition of its key range by quadrant
-// (UL, UR, BL, BR = !(x < mx) + 2 * !(y < my)), child sizes to out_cnt[4].  perm2 is scratch for the range.
-__device__ void warp_split(TreeSmem& s, int id, unsigned short* out_cnt) {
+// One warp partitions node `id` (ExtractorNode::DivideNode): stable 4-way partition of its key range by quadrant
+// (UL, UR, BL, BR = !(x < mx) + 2 * !(y < my)) into perm2, child sizes to out_cnt[4].  warp_commit() copies the range back to
+// perm: a node that ends up NOT being split (last phase, past the cut-off) keeps its key order, which decides response ties.
+__device__ void warp_partition(TreeSmem& s, int id, unsigned short* out_cnt) {
   const int lane = threadIdx.x & 31;
   const TreeNode nd = s.node[id];
   const int mx = nd.ulx + ceil_half(nd.urx - nd.ulx), my = nd.uly + ceil_half(nd.bry - nd.uly);
@@ -108,10 +108,13 @@ __device__ void warp_split(TreeSmem& s, int id, unsigned short* out_cnt) {
       off[j] += __popc(b);
     }
   }
-  __syncwarp();
-  for (int i = lane; i < nd.count; i += 32) s.perm[nd.begin + i] = s.perm2[nd.begin + i];
-  __syncwarp();
   if (lane < 4) out_cnt[lane] = static_cast<unsigned short>(c[lane]);
+  __syncwarp();
+}
+__device__ void warp_commit(TreeSmem& s, int id) {
+  const int lane = threadIdx.x & 31;
+  const int b = s.node[id].begin, n = s.node[id].count;
+  for (int i = lane; i < n; i += 32) s.perm[b + i] = s.perm2[b + i];
   __syncwarp();
 }
 
@@ -133,27 +136,67 @@ __device__ __forceinline__ TreeNode child_of(const TreeNode& p, int q, int start
 // cand: packed x | y << 12 | response << 24 (k_cells), all levels, level l at [level_off[l], level_off[l + 1]).
 // out_sel[l * kTreeSelCap + i]: packed candidate of the i-th retained keypoint of level l (list order); out_count[l].
 // A level that does not fit the shared-memory caps sets bit l of *out_error (the host then takes its own path).
+// Input either as the compacted candidate array (cand / level_off) or -- cell_items != nullptr -- straight from the per-cell lists
+// k_cells wrote (cell c of the level holds cell_count[c] items at cell_items[c * kCellCap ...]; cells in row-major order, which is
+// the reference's vToDistributeKeys order), sparing the scan / gather launches.
 __global__ void __launch_bounds__(kTreeThreads, 1)
-k_distribute(const uint32_t* __restrict__ cand, const int* __restrict__ level_off, OrbTreeParams prm, uint32_t* __restrict__ out_sel,
-             int* __restrict__ out_count, int* __restrict__ out_error) {
+k_distribute(const uint32_t* __restrict__ cand, const int* __restrict__ level_off, const uint32_t* __restrict__ cell_items,
+             const int* __restrict__ cell_count, OrbTreeParams prm, uint32_t* __restrict__ out_sel, int* __restrict__ out_count,
+             int* __restrict__ out_error) {
+  ORB_PDL_PROLOGUE();
   extern __shared__ __align__(16) uint8_t tree_raw[];
   TreeSmem& s = *reinterpret_cast<TreeSmem*>(tree_raw);
   const int l = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b0 = level_off[l], m = level_off[l + 1] - b0;
   const int n_target = prm.n_target[l], n_ini = prm.n_ini[l];
   const float hx = prm.hx[l];
+  int m;
+  if (cell_items) {
+    // exclusive scan of the level's cell counts (cells may outnumber the threads: strided passes), then one warp per cell
+    const int c0 = prm.cell_begin[l], nc = prm.cell_end[l] - c0;
+    int total = 0;
+    bool too_many = false;
+    for (int base_c = 0; base_c < nc; base_c += kTreeThreads) {
+      const int c = base_c + tid;
+      const int n = c < nc ? min(cell_count[c0 + c], kCellCap) : 0;
+      int t;
+      const int off = total + block_exscan(n, s.scan, &t);
+      if (c < nc && c < kTreeNodeCap) s.seq2node[c] = static_cast<unsigned short>(min(off, 65535));  // scratch: the cell's offset
+      total += t;
+      if (nc > kTreeNodeCap) too_many = true;
+    }
+    m = total;
+    if (m > kTreeKeyCap || too_many) {
+      if (tid == 0) { out_count[l] = 0; atomicOr(out_error, 1 << l); }
+      return;
+    }
+    __syncthreads();
+    for (int c = warp; c < nc; c += kTreeWarps) {
+      const int n = min(cell_count[c0 + c], kCellCap), off = s.seq2node[c];
+      for (int i = lane; i < n; i += 32) {
+        const uint32_t v = cell_items[static_cast<size_t>(c0 + c) * kCellCap + i];
+        s.kx[off + i] = static_cast<unsigned short>(v & 0xFFF);
+        s.ky[off + i] = static_cast<unsigned short>((v >> 12) & 0xFFF);
+        s.kr[off + i] = static_cast<unsigned char>(v >> 24);
+      }
+    }
+    __syncthreads();
+  } else {
+    const int b0 = level_off[l];
+    m = level_off[l + 1] - b0;
+    if (m > 0 && m <= kTreeKeyCap)
+      for (int k = tid; k < m; k += kTreeThreads) {
+        const uint32_t c = cand[b0 + k];
+        s.kx[k] = static_cast<unsigned short>(c & 0xFFF);
+        s.ky[k] = static_cast<unsigned short>((c >> 12) & 0xFFF);
+        s.kr[k] = static_cast<unsigned char>(c >> 24);
+      }
+  }
   if (m <= 0) { if (tid == 0) out_count[l] = 0; return; }
   if (m > kTreeKeyCap || n_ini > 16 || n_target + 8 > kTreeSelCap) {
     if (tid == 0) { out_count[l] = 0; atomicOr(out_error, 1 << l); }
     return;
   }
-  // ---- keys; initial cells: stable counting sort by int(x / hx), clamped (ORBextractor.cc:551-575)
-  for (int k = tid; k < m; k += kTreeThreads) {
-    const uint32_t c = cand[b0 + k];
-    s.kx[k] = static_cast<unsigned short>(c & 0xFFF);
-    s.ky[k] = static_cast<unsigned short>((c >> 12) & 0xFFF);
-    s.kr[k] = static_cast<unsigned char>(c >> 24);
-  }
+  // ---- initial cells: stable counting sort by int(x / hx), clamped (ORBextractor.cc:551-575)
   if (tid < kTreeWarps * 16) (&s.warp_cnt[0][0])[tid] = 0;
   if (tid == 0) { s.error = 0; s.finish = 0; }
   __syncthreads();
@@ -220,7 +263,7 @@ k_distribute(const uint32_t* __restrict__ cand, const int* __restrict__ level_of
     // (1) every splittable node of the list is partitioned, one warp per node
     for (int i = warp; i < S; i += kTreeWarps) {
       const int id = s.base[i];
-      if (!s.node[id].no_more) warp_split(s, id, s.cnt[i]);
+      if (!s.node[id].no_more) { warp_partition(s, id, s.cnt[i]); warp_commit(s, id); }
     }
     __syncthreads();
     const int n_nodes0 = s.n_nodes, seq0 = s.seq;
@@ -300,77 +343,94 @@ k_distribute(const uint32_t* __restrict__ cand, const int* __restrict__ level_of
     if (S_new + 3 * tot_sp > n_target) { last_phase = true; break; }      // (:663)
   }
 
-  // ---- last phase (:665-732): largest nodes first, one split at a time, until the target is reached
+  // ---- last phase (:665-732): largest nodes first, one split at a time, until the target is reached.  Sequential in the
+  // reference; here every node of the round is partitioned tentatively (in parallel, into perm2), the gains (children - 1) are
+  // prefix-summed in processing order, the first position that reaches the target is the cut-off, and only the splits up to it
+  // are committed -- children, creation sequence numbers and list positions follow from the same prefix sums.
   while (last_phase) {
     const int R = s.n_pend, prev = s.size;
-    // sort the round by (count, seq) ascending (std::sort on (size, pointer) pairs in the reference; ties by creation order here)
-    int P = 1;
-    while (P < R) P <<= 1;
-    for (int i = tid; i < P; i += kTreeThreads)
-      s.sortkey[i] = i < R ? (static_cast<unsigned>(s.node[s.pend[i]].count) << 16) | s.node[s.pend[i]].seq : 0xFFFFFFFFu;
+    // processing order = descending (count, seq) (std::sort on (size, pointer) pairs in the reference; ties by creation order
+    // here): rank sort, the keys are unique
+    for (int i = tid; i < R; i += kTreeThreads)
+      s.sortkey[i] = (static_cast<unsigned>(s.node[s.pend[i]].count) << 16) | s.node[s.pend[i]].seq;
     __syncthreads();
-    for (int k = 2; k <= P; k <<= 1)
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < P; i += kTreeThreads) {
-          const int ixj = i ^ j;
-          if (ixj > i) {
-            const unsigned a = s.sortkey[i], b = s.sortkey[ixj];
-            const bool up = (i & k) == 0;
-            if ((a > b) == up) { s.sortkey[i] = b; s.sortkey[ixj] = a; }
-          }
-        }
-        __syncthreads();
-      }
-    if (warp == 0) {
-      int size = s.size, n_nodes = s.n_nodes, seq = s.seq, nf = s.n_front, np2 = 0;
-      bool overflow = false;
-      for (int j = R - 1; j >= 0; --j) {
-        const int id = s.seq2node[s.sortkey[j] & 0xFFFFu];
-        warp_split(s, id, s.c4);
-        const TreeNode par = s.node[id];
-        int start = 0, made = 0;
+    for (int i = tid; i < R; i += kTreeThreads) {
+      const unsigned key = s.sortkey[i];
+      int larger = 0;
+      for (int j = 0; j < R; ++j) larger += s.sortkey[j] > key;
+      s.base2[larger] = s.pend[i];  // base2[p] = the p-th node to be processed
+    }
+    if (tid == 0) s.finish = R;  // cut-off position (exclusive bound on committed splits), lowered below
+    __syncthreads();
+    for (int p = warp; p < R; p += kTreeWarps) warp_partition(s, s.base2[p], s.cnt[p]);
+    __syncthreads();
+    // cut-off: first p with size + sum_{p' <= p} (children(p') - 1) >= target
+    int run_gain = 0;
+    for (int base_p = 0; base_p < R; base_p += kTreeThreads) {
+      const int p2 = base_p + tid;
+      int gain = 0;
+      if (p2 < R) { for (int q = 0; q < 4; ++q) gain += s.cnt[p2][q] > 0; gain -= 1; }
+      int t;
+      const int exc = block_exscan(gain, s.scan, &t);
+      if (p2 < R && prev + run_gain + exc + gain >= n_target) atomicMin(&s.finish, p2 + 1);
+      run_gain += t;
+    }
+    __syncthreads();
+    const int Cn = s.finish;  // splits 0 .. Cn-1 are committed
+    const int n_nodes0 = s.n_nodes, seq0 = s.seq, nf0 = s.n_front;
+    int tot_ch = 0, tot_sp = 0;
+    bool overflow = false;
+    for (int base_p = 0; base_p < Cn; base_p += kTreeThreads) {
+      const int p2 = base_p + tid;
+      int nch = 0, nsp = 0;
+      if (p2 < Cn) for (int q = 0; q < 4; ++q) { nch += s.cnt[p2][q] > 0; nsp += s.cnt[p2][q] > 1; }
+      int t_ch, t_sp;
+      const int e_ch = block_exscan(nch, s.scan, &t_ch);
+      const int e_sp = block_exscan(nsp, s.scan, &t_sp);
+      if (n_nodes0 + tot_ch + t_ch > kTreeNodeCap || nf0 + tot_ch + t_ch > kTreeListCap || tot_sp + t_sp > kTreeListCap) overflow = true;
+      if (p2 < Cn && !overflow) {
+        const int pid = s.base2[p2];
+        const TreeNode par = s.node[pid];
+        int g = tot_ch + e_ch, sp = tot_sp + e_sp, start = 0;
         for (int q = 0; q < 4; ++q) {
-          const int c = s.c4[q];
+          const int c = s.cnt[p2][q];
           if (c) {
-            if (n_nodes >= kTreeNodeCap || nf >= kTreeListCap || np2 >= kTreeListCap) { overflow = true; break; }
-            if (lane == 0) {
-              TreeNode ch = child_of(par, q, start, c);
-              if (c > 1) {
-                ch.seq = static_cast<unsigned short>(seq + 1);
-                s.seq2node[seq + 1] = static_cast<unsigned short>(n_nodes);
-                s.pend2[np2] = static_cast<unsigned short>(n_nodes);
-              }
-              s.node[n_nodes] = ch;
-              s.front[nf] = static_cast<unsigned short>(n_nodes);  // push_front
+            TreeNode ch = child_of(par, q, start, c);
+            const int cid = n_nodes0 + g;
+            if (c > 1) {
+              ch.seq = static_cast<unsigned short>(seq0 + sp + 1);
+              s.seq2node[ch.seq] = static_cast<unsigned short>(cid);
+              s.pend2[sp] = static_cast<unsigned short>(cid);
+              ++sp;
             }
-            if (c > 1) { ++seq; ++np2; }
-            ++n_nodes; ++nf; ++made;
+            s.node[cid] = ch;
+            s.front[nf0 + g] = static_cast<unsigned short>(cid);  // push_front, in processing order
+            ++g;
           }
           start += c;
         }
-        if (overflow) break;
-        if (lane == 0) s.node[id].alive = 0;  // erase
-        size += made - 1;
-        __syncwarp();
-        if (size >= n_target) break;
+        s.node[pid].alive = 0;  // erase
       }
-      if (lane == 0) {
-        s.size = size; s.n_nodes = n_nodes; s.seq = seq; s.n_front = nf; s.n_pend2 = np2;
-        if (overflow) s.error = 1;
-        s.finish = (size >= n_target || size == prev || overflow) ? 1 : 0;
-      }
+      tot_ch += t_ch; tot_sp += t_sp;
     }
     __syncthreads();
-    if (s.error) {
+    if (overflow) {
       if (tid == 0) { atomicOr(out_error, 1 << l); out_count[l] = 0; }
       return;
     }
-    if (s.finish) break;
-    const int np2 = s.n_pend2;
+    for (int p = warp; p < Cn; p += kTreeWarps) warp_commit(s, s.base2[p]);  // the parents' ranges, now their children's
+    const int size_new = prev + tot_ch - Cn;
     __syncthreads();
-    for (int i = tid; i < np2; i += kTreeThreads) s.pend[i] = s.pend2[i];
-    if (tid == 0) s.n_pend = np2;
+    for (int i = tid; i < tot_sp; i += kTreeThreads) s.pend[i] = s.pend2[i];
+    if (tid == 0) {
+      s.n_nodes = n_nodes0 + tot_ch;
+      s.seq = seq0 + tot_sp;
+      s.n_front = nf0 + tot_ch;
+      s.size = size_new;
+      s.n_pend = tot_sp;
+    }
     __syncthreads();
+    if (size_new >= n_target || size_new == prev) break;
   }
 
   // ---- output (:735-748): list = reverse(front) ++ base, alive nodes only; per node the first key with the largest response
@@ -403,44 +463,6 @@ k_distribute(const uint32_t* __restrict__ cand, const int* __restrict__ level_of
   }
 }
 
-// Level-major concatenation of the per-level selections: OrbSelected (level coordinates, for k_describe) and the finished
-// keypoint records (ComputeKeyPointsOctTree :824-835 + the final scaling of operator() :1071-1078); angle is filled by k_describe.
-__global__ void k_finalize_keypoints(const uint32_t* __restrict__ sel_packed, const int* __restrict__ level_count, OrbTreeParams prm,
-                                     int nlevels, int cap, OrbSelected* __restrict__ sel, sivo_keypoint* __restrict__ kps,
-                                     int* __restrict__ n_out, long long* __restrict__ n_out_i64, int* __restrict__ out_error) {
-  __shared__ int off[kOrbMaxLevels + 1];
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int l = 0; l < nlevels; ++l) { off[l] = run; run += level_count[l]; }
-    off[nlevels] = run;
-    if (run > cap) { atomicOr(out_error, 1 << 30); run = 0; off[nlevels] = 0; }
-    *n_out = run;
-    if (n_out_i64) *n_out_i64 = run;
-  }
-  __syncthreads();
-  if (off[nlevels] == 0) return;
-  for (int l = 0; l < nlevels; ++l) {
-    const int n = off[l + 1] - off[l];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint32_t c = sel_packed[l * kTreeSelCap + i];
-      const int x = static_cast<int>(c & 0xFFF) + prm.min_b, y = static_cast<int>((c >> 12) & 0xFFF) + prm.min_b;
-      OrbSelected sk;
-      sk.x = static_cast<short>(x); sk.y = static_cast<short>(y); sk.level = static_cast<short>(l); sk.pad = 0;
-      sel[off[l] + i] = sk;
-      sivo_keypoint kp;
-      kp.x = static_cast<float>(x);
-      kp.y = static_cast<float>(y);
-      if (l != 0) { kp.x = __fmul_rn(kp.x, prm.scale[l]); kp.y = __fmul_rn(kp.y, prm.scale[l]); }
-      kp.size = prm.size[l];
-      kp.angle = -1.f;
-      kp.response = static_cast<float>(c >> 24);
-      kp.octave = l;
-      kp.class_id = -1;
-      kps[off[l] + i] = kp;
-    }
-  }
-}
-
 }  // namespace
 
 void orb_tree_configure() {
@@ -448,15 +470,10 @@ void orb_tree_configure() {
   SIVO_CUDA(cudaFuncSetAttribute(k_distribute, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TreeSmem))));
 }
 
-void orb_launch_distribute(const uint32_t* cand, const int* level_off, const OrbTreeParams& prm, int nlevels, uint32_t* sel_packed,
-                           int* level_count, int* error, cudaStream_t s) {
-  k_distribute<<<nlevels, kTreeThreads, sizeof(TreeSmem), s>>>(cand, level_off, prm, sel_packed, level_count, error);
-  SIVO_CUDA(cudaGetLastError());
-}
-
-void orb_launch_finalize(const uint32_t* sel_packed, const int* level_count, const OrbTreeParams& prm, int nlevels, int cap,
-                         OrbSelected* sel, sivo_keypoint* kps, int* n_out, long long* n_out_i64, int* error, cudaStream_t s) {
-  k_finalize_keypoints<<<1, 256, 0, s>>>(sel_packed, level_count, prm, nlevels, cap, sel, kps, n_out, n_out_i64, error);
+void orb_launch_distribute(const uint32_t* cand, const int* level_off, const uint32_t* cell_items, const int* cell_count,
+                           const OrbTreeParams& prm, int nlevels, uint32_t* sel_packed, int* level_count, int* error, cudaStream_t s) {
+  orb_launch_pdl(k_distribute, dim3(nlevels), dim3(kTreeThreads), sizeof(TreeSmem), s, cand, level_off, cell_items, cell_count, prm, sel_packed,
+                 level_count, error);
   SIVO_CUDA(cudaGetLastError());
 }
 

@@ -404,7 +404,7 @@ SegNet::SegNet(const std::string& prototxt, const std::string& caffemodel, const
   SIVO_CUDA(cudaSetDevice(device_));
   SIVO_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   try {  // a malformed model throws out of build(): the destructor does not run for a half-built object
-    d_frame_.alloc(sizeof(uint64_t));
+    d_frame_.alloc(sizeof(FrameArgs));
     build(net, weights);
   } catch (...) {
     cudaStreamDestroy(stream_);
@@ -439,12 +439,12 @@ void SegNet::enqueue(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_
     Op& op = ops_[i];
     switch (op.kind) {
       case Op::Input:
-        launch_input_u8(bgr_dev, tensors_[op.out]->v, s);
+        launch_input_u8(bgr_dev, tensors_[op.out]->v, s, d_frame_.as<FrameArgs>());
         break;
       case Op::Expand:
       case Op::InputPad8:
         if (op.kind == Op::InputPad8)
-          launch_input_lrn_pad8(bgr_dev, tensors_[op.out]->v, op.lrn_size, op.lrn_alpha, op.lrn_beta, op.lrn_k, s);
+          launch_input_lrn_pad8(bgr_dev, tensors_[op.out]->v, op.lrn_size, op.lrn_alpha, op.lrn_beta, op.lrn_k, s, d_frame_.as<FrameArgs>());
         else if (op.expand_blk) launch_expand_taps(tensors_[op.in]->v, tensors_[op.out]->v, op.k, op.expand_blk, s);
         else launch_pad8(tensors_[op.in]->v, tensors_[op.out]->v, s);
         break;
@@ -498,7 +498,8 @@ void SegNet::enqueue(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_
       case Op::Reduce: {
         if (skip_reduce_) break;
         const TensorView& lv = tensors_[op.in]->v;
-        launch_mc_reduce(static_cast<const float*>(lv.p), lv.n, lv.c, lv.cs, lv.h * lv.w, classes_dev, conf_dev, ent_dev, s);
+        launch_mc_reduce(static_cast<const float*>(lv.p), lv.n, lv.c, lv.cs, lv.h * lv.w, classes_dev, conf_dev, ent_dev, s, 0, -1,
+                         d_frame_.as<FrameArgs>());
         break;
       }
     }
@@ -548,8 +549,13 @@ void SegNet::run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* co
   SIVO_CUDA(cudaSetDevice(device_));
   if (!s) s = stream_;
   last_classes_ = classes_dev; last_conf_ = conf_dev; last_ent_ = ent_dev; last_stream_ = s;
-  // by value, outside the captured graph: pipelined callers may issue the next frame before this one has started
-  launch_set_u64(d_frame_.as<uint64_t>(), frame_++, s);
+  // Everything that changes per frame -- the dropout frame counter and the caller's pointers -- goes to the device by value,
+  // outside the captured graph (pipelined callers may issue the next frame before this one has started), so one graph per
+  // stream serves every pointer set a caller cycles through
+  FrameArgs fa;
+  fa.frame = frame_++;
+  fa.bgr = bgr_dev; fa.classes = classes_dev; fa.conf = conf_dev; fa.ent = ent_dev;
+  launch_set_frame_args(d_frame_.as<FrameArgs>(), fa, s);
   if (profiling_) {
     while (events_.size() < ops_.size() + 1) {
       cudaEvent_t e;
@@ -577,7 +583,8 @@ void SegNet::run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* co
   for (const Op& op : ops_) if (op.kind == Op::Conv && !op.use_tc) all_tc = false;  // the SIMT launcher sets attributes per launch
   static const bool graphs_enabled = [] { const char* e = std::getenv("SIVO_B200_NO_GRAPH"); return !(e && e[0] == '1'); }();
   if (graphs_enabled && graph_ok_ && all_tc) {
-    const void* key[5] = {bgr_dev, classes_dev, conf_dev, ent_dev,
+    // the graph's kernels read the image / result pointers from FrameArgs: the key is the stream (and the op-list variant) only
+    const void* key[5] = {nullptr, nullptr, nullptr, nullptr,
                           reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(s) ^ (skip_reduce_ ? 1u : 0u))};
     cudaGraphExec_t graph_exec_ = nullptr;
     for (size_t i = 0; i < graphs_.size(); ++i)

@@ -20,9 +20,10 @@ template <> __device__ __forceinline__ void st_act<float>(float* p, float v) { *
 // ---- input: wrapInputLayer + preprocessImage (bayesian_segnet.cpp:119-140,164-178): u8 BGR -> float, no
 // mean / scale, planar split.  Here: one NHWC pixel of 4 channels (B, G, R, 0).
 template <typename AT>
-__global__ void k_input_u8(const uint8_t* __restrict__ bgr, AT* __restrict__ out, int npix) {
+__global__ void k_input_u8(const uint8_t* __restrict__ bgr, AT* __restrict__ out, int npix, const FrameArgs* __restrict__ args) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
+  if (args) bgr = args->bgr;
   const uint8_t* s = bgr + 3 * static_cast<size_t>(i);
   AT* d = out + 4 * static_cast<size_t>(i);
   st_act(d + 0, static_cast<float>(s[0]));
@@ -279,7 +280,8 @@ __global__ void k_dropout_bits(uint64_t seed, const uint64_t* frame, int layer, 
 // -sum p log2 p with 0 log 0 := 0 (computeEntropy :38-44).  One thread per pixel; `prob` never exists.
 template <int C>
 __global__ void k_mc_reduce(const float* __restrict__ logits, int T, int cs, int hw, uint8_t* __restrict__ classes,
-                            double* __restrict__ conf, double* __restrict__ entropy) {
+                            double* __restrict__ conf, double* __restrict__ entropy, const FrameArgs* __restrict__ args) {
+  if (args) { classes = args->classes; conf = args->conf; entropy = args->ent; }
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= hw) return;
   double acc[C];
@@ -325,7 +327,9 @@ __global__ void k_mc_reduce(const float* __restrict__ logits, int T, int cs, int
 // sample and there are 4x more threads in flight, which is what this HBM-bound pass needs.  The softmax max / sum and
 // the final argmax / entropy are combined with xor-shuffles inside the 4-lane group (first maximum still wins).
 __global__ void k_mc_reduce_quad(const float* __restrict__ logits, int T, int C, int hw, uint8_t* __restrict__ classes,
-                                 double* __restrict__ conf, double* __restrict__ entropy, int pix0, int pix_end) {
+                                 double* __restrict__ conf, double* __restrict__ entropy, int pix0, int pix_end,
+                                 const FrameArgs* __restrict__ args) {
+  if (args) { classes = args->classes; conf = args->conf; entropy = args->ent; }
   // Instruction diet (ncu: the first version was issue-bound at 3400 instructions per warp, 0.8 TB/s): one IEEE
   // reciprocal per sample instead of C divisions (p = e * (1/sum), <= 1 ulp from e/sum), mean = acc * (1/T) in double,
   // and log2 evaluated in float on the double mean (relative error < 2^-22, i.e. < 1e-6 on the entropy, against the
@@ -391,7 +395,8 @@ __global__ void k_mc_reduce_quad(const float* __restrict__ logits, int T, int C,
 
 __global__ void k_mc_reduce_generic(const float* __restrict__ logits, int T, int C, int cs, int hw,
                                     uint8_t* __restrict__ classes, double* __restrict__ conf,
-                                    double* __restrict__ entropy) {
+                                    double* __restrict__ entropy, const FrameArgs* __restrict__ args) {
+  if (args) { classes = args->classes; conf = args->conf; entropy = args->ent; }
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= hw) return;
   double best = -1.0, ent = 0.0;
@@ -471,7 +476,8 @@ __global__ void k_pad8(const uint2* __restrict__ in, uint4* __restrict__ out, in
 // k_input_u8 -> k_lrn<__half> -> k_pad8 in one pass over the padded image: identical operations on identical values
 // (the u8 -> half conversion is exact, the LRN output is rounded to half once), hence bitwise the same operand.
 __global__ void k_input_lrn_pad8(const uint8_t* __restrict__ bgr, uint4* __restrict__ out, int H, int W, int size,
-                                 float alpha_over_size, float beta, float k) {
+                                 float alpha_over_size, float beta, float k, const FrameArgs* __restrict__ args) {
+  if (args) bgr = args->bgr;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int Wp = W + 8;
   if (i >= static_cast<size_t>(H) * Wp) return;
@@ -579,9 +585,9 @@ void conv_dispatch(const ConvParams& p, cudaStream_t s) {
     else { using AT = float; __VA_ARGS__; }               \
   } while (0)
 
-void launch_input_u8(const uint8_t* bgr, TensorView out, cudaStream_t s) {
+void launch_input_u8(const uint8_t* bgr, TensorView out, cudaStream_t s, const FrameArgs* args) {
   int npix = out.h * out.w;
-  DISPATCH_AT(out.dt, (k_input_u8<AT><<<blocks_for(npix, 256), 256, 0, s>>>(bgr, static_cast<AT*>(out.p), npix)));
+  DISPATCH_AT(out.dt, (k_input_u8<AT><<<blocks_for(npix, 256), 256, 0, s>>>(bgr, static_cast<AT*>(out.p), npix, args)));
   SIVO_CUDA(cudaGetLastError());
 }
 
@@ -636,11 +642,12 @@ void launch_pad8(TensorView in, TensorView out, cudaStream_t s) {
   SIVO_CUDA(cudaGetLastError());
 }
 
-void launch_input_lrn_pad8(const uint8_t* bgr, TensorView out, int size, float alpha, float beta, float k, cudaStream_t s) {
+void launch_input_lrn_pad8(const uint8_t* bgr, TensorView out, int size, float alpha, float beta, float k, cudaStream_t s,
+                           const FrameArgs* args) {
   if (out.dt != DType::F16 || out.cs != 8 || out.n != 1) fail(SIVO_EINVAL, "input_lrn_pad8: unexpected tensor layout");
   const size_t total = static_cast<size_t>(out.h) * out.w;
   k_input_lrn_pad8<<<blocks_for(total, 256), 256, 0, s>>>(bgr, static_cast<uint4*>(out.p), out.h, out.w - 8, size,
-                                                          alpha / static_cast<float>(size), beta, k);
+                                                          alpha / static_cast<float>(size), beta, k, args);
   SIVO_CUDA(cudaGetLastError());
 }
 
@@ -669,9 +676,9 @@ __global__ void k_split_hilo(const float4* __restrict__ in, uint2* __restrict__ 
 
 // The frame counter the dropout kernels read travels as a kernel argument (by value): an asynchronous copy from a single
 // pinned slot could be overwritten by the next run_device() before it executes, giving two frames the same masks.
-__global__ void k_set_u64(uint64_t* dst, uint64_t v) { *dst = v; }
-void launch_set_u64(uint64_t* dst, uint64_t v, cudaStream_t s) {
-  k_set_u64<<<1, 1, 0, s>>>(dst, v);
+__global__ void k_set_frame_args(FrameArgs* dst, FrameArgs v) { *dst = v; }
+void launch_set_frame_args(FrameArgs* dst, const FrameArgs& v, cudaStream_t s) {
+  k_set_frame_args<<<1, 1, 0, s>>>(dst, v);
   SIVO_CUDA(cudaGetLastError());
 }
 
@@ -725,18 +732,18 @@ void launch_dropout_unpool(TensorView in, int T, const uint8_t* mask, int mask_n
 }
 
 void launch_mc_reduce(const float* logits, int T, int C, int cs, int hw, uint8_t* classes, double* conf, double* entropy,
-                      cudaStream_t s, int pix0, int npix) {
+                      cudaStream_t s, int pix0, int npix, const FrameArgs* args) {
   if (npix < 0) { pix0 = 0; npix = hw; }
   if (pix0 < 0 || pix0 + npix > hw) fail(SIVO_EINVAL, "mc_reduce: pixel range outside the map");
   if (npix == 0) return;
   if (cs == 16 && C <= 16) {
-    k_mc_reduce_quad<<<blocks_for(static_cast<size_t>(npix) * 4, 256), 256, 0, s>>>(logits, T, C, hw, classes, conf, entropy, pix0, pix0 + npix);
+    k_mc_reduce_quad<<<blocks_for(static_cast<size_t>(npix) * 4, 256), 256, 0, s>>>(logits, T, C, hw, classes, conf, entropy, pix0, pix0 + npix, args);
     SIVO_CUDA(cudaGetLastError());
     return;
   }
   if (pix0 != 0 || npix != hw) fail(SIVO_EINVAL, "mc_reduce: pixel ranges need the 16-channel logits layout");
-  if (C == 15) k_mc_reduce<15><<<blocks_for(hw, 128), 128, 0, s>>>(logits, T, cs, hw, classes, conf, entropy);
-  else k_mc_reduce_generic<<<blocks_for(hw, 128), 128, 0, s>>>(logits, T, C, cs, hw, classes, conf, entropy);
+  if (C == 15) k_mc_reduce<15><<<blocks_for(hw, 128), 128, 0, s>>>(logits, T, cs, hw, classes, conf, entropy, args);
+  else k_mc_reduce_generic<<<blocks_for(hw, 128), 128, 0, s>>>(logits, T, C, cs, hw, classes, conf, entropy, args);
   SIVO_CUDA(cudaGetLastError());
 }
 

@@ -30,13 +30,25 @@ struct ConvParams {
   float slope = 0.f;
 };
 
+// What changes from frame to frame, in device memory, so that ONE captured CUDA graph serves every call: the dropout frame
+// counter and the caller's image / result pointers.  run_device() overwrites it by value (k_set_frame_args, outside the graph);
+// the kernels that touch caller memory (input conversion, MC reduction) read their pointers from it.
+struct FrameArgs {
+  uint64_t frame;        // first member: DropoutParams::frame_dev points here
+  const uint8_t* bgr;
+  uint8_t* classes;
+  double* conf;
+  double* ent;
+};
+
 struct DropoutParams {
   uint64_t seed = 0;
   const uint64_t* frame_dev = nullptr;  // device scalar, so a captured graph replays with a new frame
   int layer = 0;
 };
 
-void launch_input_u8(const uint8_t* bgr_hwc, TensorView out, cudaStream_t s);
+// `args` != nullptr: the image / result pointers are read from *args on the device instead of the by-value arguments
+void launch_input_u8(const uint8_t* bgr_hwc, TensorView out, cudaStream_t s, const FrameArgs* args = nullptr);
 void launch_lrn(TensorView in, TensorView out, int size, float alpha, float beta, float k, cudaStream_t s);
 void launch_conv_simt(const ConvParams& p, cudaStream_t s);
 // 4-channel input -> K*blk-channel tap-expanded tensor (see k_expand_taps)
@@ -49,11 +61,12 @@ void launch_keypoint_lookup(const sivo_keypoint* kps, int n, const uint8_t* clas
                             uint8_t* out_class, double* out_conf, double* out_ent, cudaStream_t s);
 void launch_pad8(TensorView in, TensorView out, cudaStream_t s);
 // the three steps input_u8 -> lrn -> pad8 in one pass (same arithmetic, so the same half values)
-void launch_input_lrn_pad8(const uint8_t* bgr, TensorView out, int size, float alpha, float beta, float k, cudaStream_t s);
+void launch_input_lrn_pad8(const uint8_t* bgr, TensorView out, int size, float alpha, float beta, float k, cudaStream_t s,
+                           const FrameArgs* args = nullptr);
 // float [px][C] -> half [px][hi C | lo C] (split-operand fp32 mode of the tensor-core convolution)
 void launch_split_hilo(TensorView in, void* out_half, cudaStream_t s);
 // *dst = v on stream s, the value passed as a kernel argument
-void launch_set_u64(uint64_t* dst, uint64_t v, cudaStream_t s);
+void launch_set_frame_args(FrameArgs* dst, const FrameArgs& v, cudaStream_t s);
 void launch_pool(TensorView in, TensorView out, uint8_t* mask, cudaStream_t s);
 // mask_n: batch of the mask tensor (1 when the pool ran in the sample-invariant prefix)
 void launch_unpool(TensorView in, const uint8_t* mask, int mask_n, TensorView out, cudaStream_t s);
@@ -62,7 +75,7 @@ void launch_dropout(TensorView in, TensorView out, const DropoutParams& d, float
 // logits: float [T, H, W, 16]
 // pix0 / npix restrict the pass to pixels [pix0, pix0 + npix) (npix < 0: all of them)
 void launch_mc_reduce(const float* logits, int T, int C, int cs, int hw, uint8_t* classes, double* conf,
-                      double* entropy, cudaStream_t s, int pix0 = 0, int npix = -1);
+                      double* entropy, cudaStream_t s, int pix0 = 0, int npix = -1, const FrameArgs* args = nullptr);
 void launch_dropout_bits(uint64_t seed, const uint64_t* frame_dev, int layer, int T, int C, int H, int W,
                          uint8_t* keep_nchw, cudaStream_t s);
 // layout converters for the test hooks (float NCHW host order <-> NHWC activation)

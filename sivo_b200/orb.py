@@ -63,34 +63,49 @@ class ORBextractor:
         ptrs = strides = None
         bufs = []
         if want_pyramid:
-            ptrs = (C.c_void_p * self.nlevels)()
-            strides = (C.c_size_t * self.nlevels)()
-            for l in range(self.nlevels):
-                w, h = C.c_int(), C.c_int()
-                L.check(L.lib().sivo_orb_level_size(self._h, rows, cols, l, C.byref(w), C.byref(h)))
-                if pyramid_buffers is not None:  # caller-owned (e.g. page-locked) storage, reused across frames
-                    b = pyramid_buffers[l]
-                    assert b.shape == (h.value + 38, w.value + 38) and b.dtype == np.uint8
-                else:
-                    b = np.empty((h.value + 38, w.value + 38), np.uint8)
-                bufs.append(b)
-                ptrs[l] = b.ctypes.data
-                strides[l] = b.strides[0]
+            # the marshalled pointer / stride arrays of caller-owned level buffers are cached per buffer set: the per-call
+            # Python work of the mirror (a dozen ctypes calls) would otherwise rival the operator's own latency
+            key = (rows, cols, id(pyramid_buffers)) if pyramid_buffers is not None else None
+            cached = getattr(self, "_pyr_cache", None)
+            if key is not None and cached is not None and cached[0] == key:
+                _, ptrs, strides, bufs, views = cached
+            else:
+                ptrs = (C.c_void_p * self.nlevels)()
+                strides = (C.c_size_t * self.nlevels)()
+                shapes = self.level_shapes(rows, cols)
+                for l in range(self.nlevels):
+                    if pyramid_buffers is not None:  # caller-owned (e.g. page-locked) storage, reused across frames
+                        b = pyramid_buffers[l]
+                        assert b.shape == shapes[l] and b.dtype == np.uint8
+                    else:
+                        b = np.empty(shapes[l], np.uint8)
+                    bufs.append(b)
+                    ptrs[l] = b.ctypes.data
+                    strides[l] = b.strides[0]
+                views = [b[19:-19, 19:-19] for b in bufs]
+                if key is not None:
+                    self._pyr_cache = (key, ptrs, strides, bufs, views)
+            self._bordered = bufs
+            self.mvImagePyramid = views
+        else:
+            self._bordered = []
+            self.mvImagePyramid = []
         L.check(L.lib().sivo_orb_run(self._h, image.ctypes.data_as(C.c_void_p), rows, cols, C.c_size_t(image.strides[0]),
                                      kps.ctypes.data_as(C.c_void_p), cap, C.byref(n), desc.ctypes.data_as(C.c_void_p),
                                      ptrs, strides))
-        self._bordered = bufs
-        self.mvImagePyramid = [b[19:-19, 19:-19] for b in bufs]
-        return kps[:n.value].copy(), desc[:n.value].copy()
+        return kps[:n.value], desc[:n.value]
 
     def level_shapes(self, rows: int, cols: int):
         """Bordered level buffer shapes (h + 38, w + 38) for a rows x cols image."""
-        out = []
-        for l in range(self.nlevels):
-            w, h = C.c_int(), C.c_int()
-            L.check(L.lib().sivo_orb_level_size(self._h, rows, cols, l, C.byref(w), C.byref(h)))
-            out.append((h.value + 38, w.value + 38))
-        return out
+        cache = self.__dict__.setdefault("_shape_cache", {})
+        if (rows, cols) not in cache:
+            out = []
+            for l in range(self.nlevels):
+                w, h = C.c_int(), C.c_int()
+                L.check(L.lib().sivo_orb_level_size(self._h, rows, cols, l, C.byref(w), C.byref(h)))
+                out.append((h.value + 38, w.value + 38))
+            cache[(rows, cols)] = out
+        return list(cache[(rows, cols)])
 
     def run_device_input(self, gray_ptr: int, rows: int, cols: int, pitch: int):
         cap = self.nfeatures + 4 * self.nlevels + 64

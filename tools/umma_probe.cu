@@ -92,7 +92,10 @@ int main() {
   const int iters = 20000;
   printf("| grid | issuer warps | N | accumulators / issuer | A start row | cycles / MMA (K=16, per SM) | MAC/clk/SM | of 4096 |\n|---|---|---|---|---|---:|---:|---:|\n");
   const int cfgs[][5] = {{148, 1, 64, 1, 0}, {148, 1, 64, 4, 0}, {148, 1, 64, 4, 3}, {148, 2, 64, 2, 0}, {148, 2, 64, 4, 0}, {148, 1, 128, 2, 0},
-                         {148, 2, 128, 2, 0}, {148, 1, 256, 2, 0}, {148, 2, 256, 1, 0}, {1, 2, 64, 2, 0}};
+                         {148, 2, 128, 2, 0}, {148, 1, 256, 2, 0}, {148, 2, 256, 1, 0}, {1, 2, 64, 2, 0},
+                         // round 2: the widths the stacked-tap kernels issue (N = 16 x rows fed, up to 112; 192 for the triple group)
+                         {148, 1, 16, 1, 0}, {148, 1, 32, 1, 0}, {148, 1, 48, 1, 0}, {148, 1, 80, 1, 0}, {148, 1, 96, 1, 0}, {148, 1, 112, 1, 0},
+                         {148, 1, 112, 1, 3}, {148, 1, 112, 4, 0}, {148, 1, 192, 1, 0}, {148, 1, 192, 2, 0}};
   for (auto& c : cfgs) {
     if (c[1] * c[2] * c[3] > 512) continue;
     probe<<<c[0], 128, smem>>>(c[2], iters, c[3], c[4], c[1], d);
