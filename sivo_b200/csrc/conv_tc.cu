@@ -237,7 +237,7 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, const TcConsts& 
     if (p.dbg_noepi == 3) x += 1 << 20;  // every store is predicated off by the x < W test
     const int cl = lane & 3;          // this lane's 16-byte chunk after the transpose
     const int xg = x - cl;            // first pixel of the lane's group of four
-    const bool row_ok = y < p.H;
+    const bool row_ok = y < p.H && img < p.N_batch;  // img >= N: the odd image out of an image-pair tile (PK2)
     if (p.out_f32 == 1) {  // 16-channel float logits (the convolution feeding Softmax)
       uint32_t v[32];
       tmem_ld16(trow, v);
@@ -367,7 +367,7 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, const TcConsts& 
 // unfused path would store) -> 2x2 max with first-maximum argmax; the horizontal neighbour lives in the adjacent lane.
 __device__ __forceinline__ void epilogue_pool_rows(const TcParams& p, const TcConsts& cst, uint32_t trow0, uint32_t trow1, int img, int y, int x, int n0, int lane) {
   if (p.dbg_noepi) return;
-  const bool writer = (lane & 1) == 0 && y + 1 < p.H && x + 1 < p.W;
+  const bool writer = (lane & 1) == 0 && y + 1 < p.H && x + 1 < p.W && img < p.N_batch;
   for (int cc = 0; cc < p.n_tile; cc += 32) {
     uint32_t v0[32], v1[32];
     tmem_ld32(trow0 + cc, v0);
@@ -426,7 +426,13 @@ __device__ __forceinline__ void epilogue_pool_rows(const TcParams& p, const TcCo
 //               the K*K taps and released; the ring double-buffers chunks.
 // KW < K : the kernel is K x KW over a *window-folded* input (KW = 1: every pixel's 64 "channels" are the 8-pixel x
 //               8-channel window starting at it, so a 3-channel K x K layer is a K x 1 layer; see conv_tc_plan).
-template <int K, bool ROLL, int kRows, int KW = K>
+// PK2 (only with !ROLL): layers at most 64 pixels wide (Standard's conv5_x at 22x64) would fill half of every 128-pixel M tile.
+//               Two images share a tile instead (rows 0-63: image 2z, rows 64-127: image 2z+1), and because the kw shift of a
+//               shared-memory row would run from one image into the other, the shift is done by TMA: per (chunk, kw) the halo rows
+//               are fetched as two 64-pixel boxes starting at pixel kw - 1 (out-of-range pixels and images zero-filled), so the
+//               A operand of tap (kh, kw) is an unshifted, fully populated tile.  3x the halo traffic, which these small layers
+//               have to spare; weights arrive in (kw, kh) order.
+template <int K, bool ROLL, int kRows, int KW = K, bool PK2 = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcParams p,
           const __grid_constant__ TcConsts cst) {
@@ -453,15 +459,17 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int strip = blockIdx.x % p.strips, rowblk = blockIdx.x / p.strips;
+  static_assert(!PK2 || (!ROLL && KW == K), "image-pair tiles use the chunked kernel");
+  constexpr int UPC = PK2 ? KW * RK : RK;          // halo units per (row block, chunk)
   const int n0 = blockIdx.y * p.n_tile;
-  const int img = blockIdx.z;
+  const int img = PK2 ? 2 * blockIdx.z : blockIdx.z;
   const int x0 = strip * 128;
   const int NC = ROLL ? 1 : p.chunks;
   const int total_pairs = (p.H + kRows - 1) / kRows;
   const int pair0 = rowblk * p.pairs_per_cta;
   const int npairs = min(p.pairs_per_cta, total_pairs - pair0);
   const int y_base = pair0 * kRows;              // first output row of this CTA
-  const int n_units = ROLL ? npairs * kRows + K - 1 : npairs * NC * RK;
+  const int n_units = ROLL ? npairs * kRows + K - 1 : npairs * NC * UPC;
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(2 * kRows * p.n_tile)) tmem_cols <<= 1;
 
@@ -495,17 +503,24 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       for (int u = 0; u < n_units; ++u) {
         const int slot = u % kSlots;
         const uint32_t round = static_cast<uint32_t>(u / kSlots);
-        int ch = 0, yy;
+        int ch = 0, yy, kw_p = 0;
         if (ROLL) {
           yy = y_base - kPad + u;
         } else {
-          const int j = u / (NC * RK), rem = u % (NC * RK);
-          ch = rem / RK;
+          const int j = u / (NC * UPC), rem = u % (NC * UPC);
+          ch = rem / UPC;
+          kw_p = (rem % UPC) / RK;
           yy = y_base + j * kRows - kPad + rem % RK;
         }
         mbar_wait(a_empty + slot, (round & 1) ^ 1);
-        mbar_expect_tx(a_full + slot, static_cast<uint32_t>((128 + KW - 1) * 128));
         const int a_ch = p.split ? (ch & 1) * p.cin_real + (ch >> 1) * 64 : ch * 64;  // split: chunk = (real chunk, hi | lo plane)
+        if (PK2) {
+          mbar_expect_tx(a_full + slot, static_cast<uint32_t>(2 * 64 * 128));
+          tma_load_4d(a_slots + slot * kSlotBytes, &map_a, a_full + slot, a_ch, kw_p - kPadW, yy, img);
+          tma_load_4d(a_slots + slot * kSlotBytes + 64 * 128, &map_a, a_full + slot, a_ch, kw_p - kPadW, yy, img + 1);
+          continue;
+        }
+        mbar_expect_tx(a_full + slot, static_cast<uint32_t>((128 + KW - 1) * 128));
         tma_load_4d(a_slots + slot * kSlotBytes, &map_a, a_full + slot, a_ch, x0 - kPadW, yy, img);
       }
     }
@@ -525,7 +540,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               mbar_wait(b_empty + st, ((it / kBStages) & 1) ^ 1);
               mbar_expect_tx(b_full + st, static_cast<uint32_t>(b_bytes));
               const int kc = p.split ? (3 * (ch >> 1) + ((ch & 1) ? 2 : rep)) * 64 : ch * 64;
-              tma_load_3d(b_stages + st * b_stride, &map_b, b_full + st, kc, n0, tap + w_replica * K * KW);
+              const int tap_w = PK2 ? (tap % K) * K + tap / K : tap;  // PK2 consumes taps kw-major: (kw, kh) -> kh * K + kw
+              tma_load_3d(b_stages + st * b_stride, &map_b, b_full + st, kc, n0, tap_w + w_replica * K * KW);
             }
         }
     }
@@ -545,11 +561,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     const int S = p.split ? p.seg_rows : K;
     for (int j = 0; j < npairs; ++j) {
       int acc = seg & 1;
-      for (int ch = 0; ch < NC; ++ch) {
-        const int base_u = ROLL ? j * kRows : (j * NC + ch) * RK;
+      for (int ch = 0; ch < NC; ++ch)
+      for (int kwo = 0; kwo < (PK2 ? KW : 1); ++kwo) {  // PK2: the kw shift is done by TMA, one set of halo rows per tap column
+        const int base_u = ROLL ? j * kRows : PK2 ? ((j * NC + ch) * KW + kwo) * RK : (j * NC + ch) * RK;
         for (int kh = 0; kh < K; ++kh) {
-          const bool seg_start = p.split ? (kh % S == 0) : (ch == 0 && kh == 0);
-          const bool seg_end = p.split ? (kh % S == S - 1 || kh == K - 1) : (ch == NC - 1 && kh == K - 1);
+          const bool seg_start = p.split ? (kh % S == 0) : (ch == 0 && kwo == 0 && kh == 0);
+          const bool seg_end = p.split ? (kh % S == S - 1 || kh == K - 1) : (ch == NC - 1 && kwo == (PK2 ? KW - 1 : 0) && kh == K - 1);
           if (seg_start) {
             acc = seg & 1;
             mbar_wait(t_empty + acc, ((seg >> 1) & 1) ^ 1);
@@ -567,11 +584,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             a_row_lo[m] = (((a_base + (unit % kSlots) * kSlotBytes) & 0x3FFFFu) >> 4) | (1u << 16);
             d_row[m] = tmem_base + static_cast<uint32_t>((acc * kRows + r_first + m) * p.n_tile);
           }
-          const uint32_t first_row = p.split ? (kh % S ? 1u : 0u) : ((ch | kh) ? 1u : 0u);  // 0: the segment's first MMAs clear
-          const uint32_t kw_step = p.dbg_noshift ? 0u : 8u;
+          const uint32_t first_row = p.split ? (kh % S ? 1u : 0u) : ((ch | kwo | kh) ? 1u : 0u);  // 0: the segment's first MMAs clear
+          const uint32_t kw_step = (p.dbg_noshift || PK2) ? 0u : 8u;
           const int nrep = p.split && !(ch & 1) ? 2 : 1;
 #pragma unroll
-          for (int kw = 0; kw < KW; ++kw)
+          for (int kw = 0; kw < (PK2 ? 1 : KW); ++kw)
           for (int rep = 0; rep < nrep; ++rep) {
             mbar_wait(b_full + st, b_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -622,7 +639,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     // rows of a block between them -- halve the epilogue's duration so it fits under the MMAs again.
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int eset = (warp - 4) >> 2;  // 0: first half of the block's rows, 1: second half
-    const int x = x0 + q * 32 + lane;
+    const int x = PK2 ? ((q * 32 + lane) & 63) : x0 + q * 32 + lane;  // PK2: tile rows 64-127 are the second image
+    const int img_e = PK2 ? img + ((q * 32 + lane) >> 6) : img;
     if (!ROLL && kRows == 2 && p.split) {
       // split-operand fp32 mode: a block arrives as NC * ceil(K / seg_rows) accumulation segments; each epilogue warp owns one
       // of the block's two rows, sums the segments in registers (round-to-nearest) and finishes the row after the last one
@@ -719,7 +737,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         if (kRows == 4 || eset == 0) {  // a row pair per set (kRows == 2: one pair, taken by set 0)
           const int r = kRows == 4 ? 2 * eset : 0;
           const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
-          epilogue_pool_rows(p, cst, trow, trow + p.n_tile, img, y_base + j * kRows + r, x, n0, lane);
+          epilogue_pool_rows(p, cst, trow, trow + p.n_tile, img_e, y_base + j * kRows + r, x, n0, lane);
         }
       } else {
 #pragma unroll
@@ -727,7 +745,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           const int r = eset * kPer + rr;
           const int y = y_base + j * kRows + r;
           const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * kRows + r) * p.n_tile);
-          epilogue_row(p, cst, trow, img, y, x, n0, lane);
+          epilogue_row(p, cst, trow, img_e, y, x, n0, lane);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1179,6 +1197,7 @@ struct ConvTcPlan {
   bool pair = false;  // paired-tap kernel (64 -> 64 channels, 4-row blocks)
   bool triple = false;  // ... with taps 4..6 stacked three-high (K = 7)
   bool nw16 = false;    // ... with 16-wide accumulators: conv composed with the 1x1 classifier
+  bool pk2 = false;     // two images per 128-pixel M tile (layers at most 64 pixels wide, chunked 3x3 kernel)
   bool stack16 = false; // composed 64 -> 16 layer on the full-stack kernel (all seven tap rows stacked along N, resident weights)
   DevBuf w_replicas;  // private replicated copy of the weights (w_rep > 1)
 };
@@ -1221,6 +1240,7 @@ void conv_tc_dispatch(const ConvTcPlan& plan, cudaStream_t s, bool configure) {
   }
   else if (plan.roll && plan.rows == 4) { if (K == 7) go(k_conv_tc<7, true, 4>); else if (K == 3) go(k_conv_tc<3, true, 4>); else go(k_conv_tc<1, true, 4>); }
   else if (plan.roll) { if (K == 7) go(k_conv_tc<7, true, 2>); else if (K == 3) go(k_conv_tc<3, true, 2>); else go(k_conv_tc<1, true, 2>); }
+  else if (plan.pk2) go(k_conv_tc<3, false, 2, 3, true>);
   else { if (K == 7) go(k_conv_tc<7, false, 2>); else if (K == 3) go(k_conv_tc<3, false, 2>); else go(k_conv_tc<1, false, 2>); }
 }
 }  // namespace
@@ -1306,7 +1326,9 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
                           static_cast<cuuint64_t>(in.n)};
     cuuint64_t strides[3] = {static_cast<cuuint64_t>(in.cs) * 2, static_cast<cuuint64_t>(in.w) * in.cs * 2,
                              static_cast<cuuint64_t>(in.h) * in.w * in.cs * 2};
-    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(128 + K - 1), 1, 1};
+    const char* pk2_env = std::getenv("SIVO_B200_TC_PK2");
+    plan->pk2 = !roll && !op.split && K == 3 && in.w <= 64 && in.n >= 2 && !(pk2_env && pk2_env[0] == '0');
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(plan->pk2 ? 64 : 128 + K - 1), 1, 1};
     encode(&plan->map_a, in.p, 4, dims, strides, box);
   }
   const int n_tile = tc_pick_n(op, out, roll);
@@ -1343,7 +1365,8 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   if (const char* e = std::getenv("SIVO_B200_SPLIT_RZ")) p.rz_comp = static_cast<float>(atof(e)) * 1.1920929e-7f;
   p.strips = ceil_div(p.W, 128);
   const int cout_tiles = p.out_f32 == 1 ? 1 : op.cout_p / n_tile;
-  const int columns = p.strips * in.n * cout_tiles;
+  const int n_z = plan->pk2 ? ceil_div(in.n, 2) : in.n;  // PK2: an image pair per tile
+  const int columns = p.strips * n_z * cout_tiles;
   const int rows = tc_rows(K, roll, n_tile, columns, in.h);
   const int total_pairs = ceil_div(in.h, rows);
   // row blocks per CTA: minimise (waves of 148 SMs) x (blocks per CTA + ~1 block of prologue / halo overhead)
@@ -1376,7 +1399,7 @@ std::shared_ptr<ConvTcPlan> conv_tc_plan(const Op& op, const TensorView& in, con
   if (const char* e = std::getenv("SIVO_B200_TC_NOLOAD")) p.dbg_noload = e[0] == '1';
   p.pool_out = nullptr; p.pool_mask = nullptr;
   p.has_cls = 0; p.cls_out = nullptr;
-  plan->grid = dim3(p.strips * ceil_div(total_pairs, ppc), cout_tiles, in.n);
+  plan->grid = dim3(p.strips * ceil_div(total_pairs, ppc), cout_tiles, n_z);
   p.b_stages = tc_stages(K, roll, n_tile);
   if (const char* e = std::getenv("SIVO_B200_TC_BSTAGES")) p.b_stages = std::max(2, std::min(p.b_stages, atoi(e)));  // experiment knob
   plan->smem = tc_smem_bytes(K, roll, n_tile, p.b_stages);

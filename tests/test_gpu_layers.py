@@ -117,7 +117,9 @@ def test_conv_simt_matches_oracle(k, cin, cout, prec):
                                               (3, 256, 64, 1, 22, 64), (3, 512, 512, 2, 11, 32), (1, 128, 64, 1, 6, 130),
                                               # 4-row blocks (columns x ceil(H/4) >= 148): the paired / TRIPLE stacked-tap kernels
                                               (7, 64, 64, 2, 176, 512), (7, 64, 64, 1, 352, 300), (3, 64, 64, 1, 160, 512),
-                                              (3, 64, 64, 2, 90, 520)])
+                                              (3, 64, 64, 2, 90, 520),
+                                              # at most 64 pixels wide, Cin > 64: two images per M tile, kw shift by TMA (PK2)
+                                              (3, 128, 128, 3, 22, 64), (3, 512, 512, 12, 22, 64), (3, 256, 256, 2, 11, 33), (3, 128, 64, 5, 6, 20)])
 def test_conv_tcgen05_matches_oracle(k, cin, cout, n, h, w):
     """The tensor-core convolution against torch fp32 on identical half-rounded operands; sizes cover partial
     strips (W not a multiple of 128), an odd height, several images, both UMMA N tiles, and shapes large enough to take the

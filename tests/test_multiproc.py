@@ -37,10 +37,15 @@ def _worker(rank, world, port, steps, q):
         f = _fake_frame(fid)
         rec = np.zeros(nbytes, np.uint8)
         o = record.offsets(hw, CAP)
-        record.pack_host_part(rec, hw, CAP, fid, f["kl"], f["dl"], f["kr"], f["dr"])
-        rec[o["classes"]:o["classes"] + hw] = f["classes"].reshape(-1)
-        rec[o["confidence"]:o["confidence"] + hw * 8] = f["confidence"].view(np.uint8).reshape(-1)
-        rec[o["entropy"]:o["entropy"] + hw * 8] = f["entropy"].view(np.uint8).reshape(-1)
+        if step % 2 == 0:  # the device-record layout written piecewise (value path: maps by SegNet, the rest by the extractors)
+            record.pack_host_part(rec, hw, CAP, fid, f["kl"], f["dl"], f["kr"], f["dr"])
+            rec[o["classes"]:o["classes"] + hw] = f["classes"].reshape(-1)
+            rec[o["confidence"]:o["confidence"] + hw * 8] = f["confidence"].view(np.uint8).reshape(-1)
+            rec[o["entropy"]:o["entropy"] + hw * 8] = f["entropy"].view(np.uint8).reshape(-1)
+        else:              # the whole record from host results (N > 1 e2e path)
+            record.pack_host(rec, hw, CAP, fid, f["classes"], f["confidence"], f["entropy"], f["kl"], f["dl"], f["kr"], f["dr"])
+        # the header words the asynchronous extractors write on the device: frame id, n_left, n_right as int64 at bytes 0 / 8 / 16
+        assert tuple(int(v) for v in rec[:24].view(np.int64)) == (fid, len(f["kl"]), len(f["kr"]))
         mine = torch.from_numpy(rec)
         allr = torch.empty(nbytes * world, dtype=torch.uint8)
         dist.all_gather_into_tensor(allr, mine)
@@ -66,7 +71,7 @@ def test_frame_sharding_and_record_allgather_world2():
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, 3, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 4, q)) for r in range(2)]
     [p.start() for p in procs]
     res = [q.get(timeout=120) for _ in procs]
     [p.join(timeout=60) for p in procs]

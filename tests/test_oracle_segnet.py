@@ -156,3 +156,28 @@ def test_dedup_equals_naive(model_dir):
     b = S.forward(net, w, img, dedup=False)
     assert np.array_equal(a, b)
     assert not np.array_equal(a[0], a[1])
+
+
+def test_calibrated_synthetic_weights_keep_the_softmax_unsaturated():
+    """The committed per-layer factors (configs/synth_scales.json, tools/calibrate_synth.py) hold at other input sizes and frames:
+    activations stay O(1), the logits spread by ~2.5, and the entropy map covers most of [0, log2 15] -- the condition under which
+    the confidence / entropy parity tests compare real numbers (round 1's uncalibrated weights gave logits rms 169, entropy == 0)."""
+    import gen_prototxt
+    from sivo_b200.caffemodel import shipped_scales, synth_weights
+    from sivo_b200.prototxt import load_net
+    from sivo_b200.synth import stereo_frame
+    left, _ = stereo_frame(5)
+    for kind, (H, W) in (("basic", (64, 128)), ("standard", (64, 96))):
+        net = load_net(getattr(gen_prototxt, kind)(T=2, H=H, W=W))
+        w = synth_weights(net, 0, shipped_scales(kind))
+        img = np.ascontiguousarray(left[40:40 + H, 500:500 + W])
+        prob, blobs = S.forward(net, w, img, precision="fp32", return_blobs=True)
+        logits = blobs[net.layers[-1].bottoms[0]].numpy()
+        spread = float((logits - logits.mean(axis=1, keepdims=True)).std())
+        assert 1.5 < spread < 4.0, (kind, spread)
+        for name, b in blobs.items():
+            if b.dtype.is_floating_point and "mask" not in name and name not in ("data", "norm", "prob"):
+                rms = float((b * b).mean().sqrt())
+                assert 0.2 < rms < 5.0, (kind, name, rms)
+        _, conf, ent = S.mc_reduce(prob)
+        assert np.median(ent) > 1.0 and np.quantile(ent, 0.95) < np.log2(15) + 1e-9 and np.median(conf) < 0.9, (kind, np.median(ent))
