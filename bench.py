@@ -279,7 +279,8 @@ def main():
     if world > 1:
         # The gather overlaps the next frame's convolutions, whose grids are sized to the 148 SMs (conv_decode1: 288 CTAs = two
         # waves of 144).  A default NCCL all-gather takes a dozen SMs and would push them into a third wave, so keep it to a
-        # few channels: 6.4 MB per rank needs little bandwidth (measured at N=2: 8 channels 1278 fps, 2: 1425, 1: 1443).
+        # few channels: 3.5 MB per rank needs little bandwidth (measured at N=2 with the earlier 6.4 MB record: 8 channels 1278 fps,
+        # 2: 1425, 1: 1443).
         nch = "1" if world <= 2 else "2"  # measured: N=4 2 channels 2899 fps (default 2499); N=8 2 channels 5355, 4: 5175 (default 5013)
         os.environ.setdefault("NCCL_MAX_NCHANNELS", nch)
         os.environ.setdefault("NCCL_MAX_CTAS", nch)
@@ -359,7 +360,8 @@ def main():
             if use_async_orb:
                 orb_l.wait_event(ev_side[k].cuda_event)
                 orb_r.wait_event(ev_side[k].cuda_event)
-        seg.run_device(d_bgr[j].data_ptr(), base + o_cls, base + o_conf, base + o_ent, stream.cuda_stream)
+        # classes + the record's f32 maps straight into the record; the operator's double maps stay in d_conf / d_ent
+        seg.run_device_maps(d_bgr[j].data_ptr(), base + o_cls, d_conf.data_ptr(), d_ent.data_ptr(), base + o_conf, base + o_ent, stream.cuda_stream)
         t1 = time.perf_counter()
         out = None
         if use_async_orb:
@@ -485,6 +487,8 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     gc.enable()
+    if use_async_orb and (orb_l.device_status() or orb_r.device_status()):
+        raise SystemExit("a pyramid level exceeded the device quad tree's capacity: the asynchronous records are not valid")
     prof_value = dict(prof)  # the sustained leg and the e2e variants call device_step / the extractors again
     dev_ms = e0.elapsed_time(e1)
     elapsed = max(wall, dev_ms / 1e3)  # the ORB streams are the library's own; wall brackets everything (synced both sides)

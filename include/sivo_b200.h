@@ -81,6 +81,11 @@ int sivo_segnet_run(sivo_segnet_t* h, const uint8_t* bgr, int rows, int cols, si
  * (a cudaStream_t; NULL = the handle's own stream).  No host synchronisation. */
 int sivo_segnet_run_device(sivo_segnet_t* h, const uint8_t* bgr_device, uint8_t* classes_device,
                            double* confidence_device, double* entropy_device, void* stream);
+/* The same with additional single-precision copies of the two maps (any output may be NULL): what the packed per-frame record
+ * of the multi-GPU path carries (classes u8 + entropy f32 + confidence f32), written straight into it by the MC
+ * reduction; the double maps stay the operator's outputs (bayesian_segnet.cpp:192-203, 262-276 compute in double). */
+int sivo_segnet_run_device_maps(sivo_segnet_t* h, const uint8_t* bgr_device, uint8_t* classes_device, double* confidence_device,
+                                double* entropy_device, float* confidence_f32_device, float* entropy_f32_device, void* stream);
 /* Test hook: copies blob `name` (any top in the prototxt; needs keep_blobs) to `out` as float NCHW.
  * `*n`, `*c`, `*hh`, `*ww` receive its shape; `out` may be NULL to query the shape only. */
 int sivo_segnet_blob(sivo_segnet_t* h, const char* name, float* out, size_t cap, int* n, int* c, int* hh,

@@ -96,6 +96,15 @@ int sivo_segnet_run_device(sivo_segnet_t* h, const uint8_t* bgr_device, uint8_t*
   });
 }
 
+int sivo_segnet_run_device_maps(sivo_segnet_t* h, const uint8_t* bgr_device, uint8_t* classes_device, double* confidence_device,
+                                double* entropy_device, float* confidence_f32_device, float* entropy_f32_device, void* stream) {
+  return guarded([&] {
+    if (!h || !bgr_device) fail(SIVO_EINVAL, "null handle or image");
+    h->impl->run_device(bgr_device, classes_device, confidence_device, entropy_device, static_cast<cudaStream_t>(stream),
+                        confidence_f32_device, entropy_f32_device);
+  });
+}
+
 int sivo_segnet_blob(sivo_segnet_t* h, const char* name, float* out, size_t cap, int* n, int* c, int* hh, int* ww) {
   return guarded([&] {
     if (!h || !name) fail(SIVO_EINVAL, "null handle or name");

@@ -545,7 +545,8 @@ void SegNet::semantic_keys(const sivo_keypoint* kps, int n, int max_static_class
   if (n_keep) *n_keep = kept;
 }
 
-void SegNet::run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_dev, double* ent_dev, cudaStream_t s) {
+void SegNet::run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_dev, double* ent_dev, cudaStream_t s, float* conf32_dev,
+                        float* ent32_dev) {
   SIVO_CUDA(cudaSetDevice(device_));
   if (!s) s = stream_;
   last_classes_ = classes_dev; last_conf_ = conf_dev; last_ent_ = ent_dev; last_stream_ = s;
@@ -554,7 +555,7 @@ void SegNet::run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* co
   // stream serves every pointer set a caller cycles through
   FrameArgs fa;
   fa.frame = frame_++;
-  fa.bgr = bgr_dev; fa.classes = classes_dev; fa.conf = conf_dev; fa.ent = ent_dev;
+  fa.bgr = bgr_dev; fa.classes = classes_dev; fa.conf = conf_dev; fa.ent = ent_dev; fa.conf32 = conf32_dev; fa.ent32 = ent32_dev;
   launch_set_frame_args(d_frame_.as<FrameArgs>(), fa, s);
   if (profiling_) {
     while (events_.size() < ops_.size() + 1) {

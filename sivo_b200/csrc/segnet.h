@@ -66,7 +66,9 @@ class SegNet {
   int classes() const { return n_classes_; }
   void set_frame(uint64_t f) { frame_ = f; }
   void run_host(const uint8_t* bgr, int rows, int cols, size_t stride, uint8_t* classes, double* conf, double* ent);
-  void run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_dev, double* ent_dev, cudaStream_t s);
+  // conf32 / ent32 (optional): single-precision copies of the two maps, e.g. straight into the packed multi-GPU record
+  void run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_dev, double* ent_dev, cudaStream_t s, float* conf32_dev = nullptr,
+                  float* ent32_dev = nullptr);
   void semantic_keys(const sivo_keypoint* kps, int n, int max_static_class, uint8_t* kp_class, double* kp_conf, double* kp_entropy,
                      int* keep_idx, int* n_keep);
   void blob(const std::string& name, float* out, size_t cap, int* n, int* c, int* h, int* w);

@@ -281,7 +281,8 @@ __global__ void k_dropout_bits(uint64_t seed, const uint64_t* frame, int layer, 
 template <int C>
 __global__ void k_mc_reduce(const float* __restrict__ logits, int T, int cs, int hw, uint8_t* __restrict__ classes,
                             double* __restrict__ conf, double* __restrict__ entropy, const FrameArgs* __restrict__ args) {
-  if (args) { classes = args->classes; conf = args->conf; entropy = args->ent; }
+  float *conf32 = nullptr, *ent32 = nullptr;
+  if (args) { classes = args->classes; conf = args->conf; entropy = args->ent; conf32 = args->conf32; ent32 = args->ent32; }
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= hw) return;
   double acc[C];
@@ -321,6 +322,8 @@ __global__ void k_mc_reduce(const float* __restrict__ logits, int T, int cs, int
   if (classes) classes[i] = static_cast<uint8_t>(arg);
   if (conf) conf[i] = best;
   if (entropy) entropy[i] = ent;
+  if (conf32) conf32[i] = static_cast<float>(best);
+  if (ent32) ent32[i] = static_cast<float>(ent);
 }
 
 // Same reduction with four lanes per pixel (one float4 = 4 classes each): a warp reads 512 contiguous bytes per
@@ -329,7 +332,8 @@ __global__ void k_mc_reduce(const float* __restrict__ logits, int T, int cs, int
 __global__ void k_mc_reduce_quad(const float* __restrict__ logits, int T, int C, int hw, uint8_t* __restrict__ classes,
                                  double* __restrict__ conf, double* __restrict__ entropy, int pix0, int pix_end,
                                  const FrameArgs* __restrict__ args) {
-  if (args) { classes = args->classes; conf = args->conf; entropy = args->ent; }
+  float *conf32 = nullptr, *ent32 = nullptr;
+  if (args) { classes = args->classes; conf = args->conf; entropy = args->ent; conf32 = args->conf32; ent32 = args->ent32; }
   // Instruction diet (ncu: the first version was issue-bound at 3400 instructions per warp, 0.8 TB/s): one IEEE
   // reciprocal per sample instead of C divisions (p = e * (1/sum), <= 1 ulp from e/sum), mean = acc * (1/T) in double,
   // and log2 evaluated in float on the double mean (relative error < 2^-22, i.e. < 1e-6 on the entropy, against the
@@ -358,7 +362,7 @@ __global__ void k_mc_reduce_quad(const float* __restrict__ logits, int T, int C,
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      x[j] = (q * 4 + j < C) ? expf(__fsub_rn(x[j], m)) : 0.f;
+      x[j] = (q * 4 + j < C) ? __expf(__fsub_rn(x[j], m)) : 0.f;  // ex2.approx: <= 2 ulp on an argument in [-88, 0], 2e-7 on a probability
       sum = __fadd_rn(sum, x[j]);
     }
     sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 1));
@@ -390,13 +394,16 @@ __global__ void k_mc_reduce_quad(const float* __restrict__ logits, int T, int C,
     if (classes) classes[pix] = static_cast<uint8_t>(arg);
     if (conf) conf[pix] = best;
     if (entropy) entropy[pix] = ent;
+    if (conf32) conf32[pix] = static_cast<float>(best);
+    if (ent32) ent32[pix] = static_cast<float>(ent);
   }
 }
 
 __global__ void k_mc_reduce_generic(const float* __restrict__ logits, int T, int C, int cs, int hw,
                                     uint8_t* __restrict__ classes, double* __restrict__ conf,
                                     double* __restrict__ entropy, const FrameArgs* __restrict__ args) {
-  if (args) { classes = args->classes; conf = args->conf; entropy = args->ent; }
+  float *conf32 = nullptr, *ent32 = nullptr;
+  if (args) { classes = args->classes; conf = args->conf; entropy = args->ent; conf32 = args->conf32; ent32 = args->ent32; }
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= hw) return;
   double best = -1.0, ent = 0.0;
@@ -418,6 +425,8 @@ __global__ void k_mc_reduce_generic(const float* __restrict__ logits, int T, int
   if (classes) classes[i] = static_cast<uint8_t>(arg);
   if (conf) conf[i] = best;
   if (entropy) entropy[i] = ent;
+  if (conf32) conf32[i] = static_cast<float>(best);
+  if (ent32) ent32[i] = static_cast<float>(ent);
 }
 
 // ---- tap expansion for the 3-channel first convolution: out[y][x][kh*blk + kw*4 + c] = in[y+kh-pad][x+kw-pad][c]

@@ -39,6 +39,8 @@ struct FrameArgs {
   uint8_t* classes;
   double* conf;
   double* ent;
+  float* conf32;         // optional single-precision copies of the two maps (the packed multi-GPU record carries those)
+  float* ent32;
 };
 
 struct DropoutParams {

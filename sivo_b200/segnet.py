@@ -107,6 +107,11 @@ class BayesianSegNet:
         L.check(L.lib().sivo_segnet_run_device(self._h, C.c_void_p(bgr_ptr), C.c_void_p(classes_ptr), C.c_void_p(conf_ptr),
                                                C.c_void_p(ent_ptr), C.c_void_p(stream)))
 
+    def run_device_maps(self, bgr_ptr: int, classes_ptr: int, conf_ptr: int, ent_ptr: int, conf32_ptr: int, ent32_ptr: int, stream: int = 0):
+        """run_device plus single-precision copies of the two maps (the packed multi-GPU record's layout); any pointer may be 0."""
+        L.check(L.lib().sivo_segnet_run_device_maps(self._h, C.c_void_p(bgr_ptr), C.c_void_p(classes_ptr), C.c_void_p(conf_ptr),
+                                                    C.c_void_p(ent_ptr), C.c_void_p(conf32_ptr), C.c_void_p(ent32_ptr), C.c_void_p(stream)))
+
     def blob(self, name: str) -> np.ndarray:
         n, c, h, w = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         L.check(L.lib().sivo_segnet_blob(self._h, name.encode(), None, C.c_size_t(0), C.byref(n), C.byref(c), C.byref(h), C.byref(w)))

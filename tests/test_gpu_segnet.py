@@ -200,6 +200,37 @@ def test_tcgen05_conv_equals_simt_conv_on_device(model_dir):
         assert (np.abs(a - b) > 2e-3 * scale).mean() < 1e-3, n
 
 
+def test_run_device_maps_writes_rounded_single_precision_copies(model_dir):
+    """sivo_segnet_run_device_maps: the f32 maps of the packed multi-GPU record are the operator's double maps rounded to
+    nearest, and the classes / double maps are those of segmentImage on the same frame."""
+    import torch
+    net, w, proto, model = _full_model(model_dir)
+    left, _ = stereo_frame(2)
+    seg = BayesianSegNet(BayesianSegNetParams(proto, model), seed=1234, T=2)
+    seg.set_frame(5)
+    cls, conf, ent = (np.array(a) for a in seg.segmentImage(left))
+    h, w_ = cls.shape
+    y0, x0 = (left.shape[0] - h) // 2, (left.shape[1] - w_) // 2
+    d_bgr = torch.from_numpy(np.ascontiguousarray(left[y0:y0 + h, x0:x0 + w_])).cuda()
+    d_cls = torch.empty(h * w_, dtype=torch.uint8, device="cuda")
+    d_c64, d_e64 = (torch.empty(h * w_, dtype=torch.float64, device="cuda") for _ in range(2))
+    d_c32, d_e32 = (torch.empty(h * w_, dtype=torch.float32, device="cuda") for _ in range(2))
+    seg.set_frame(5)
+    seg.run_device_maps(d_bgr.data_ptr(), d_cls.data_ptr(), d_c64.data_ptr(), d_e64.data_ptr(), d_c32.data_ptr(), d_e32.data_ptr(),
+                        torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_cls.cpu().numpy().reshape(h, w_), cls)
+    assert np.array_equal(d_c64.cpu().numpy().reshape(h, w_), conf) and np.array_equal(d_e64.cpu().numpy().reshape(h, w_), ent)
+    assert np.array_equal(d_c32.cpu().numpy(), conf.reshape(-1).astype(np.float32))
+    assert np.array_equal(d_e32.cpu().numpy(), ent.reshape(-1).astype(np.float32))
+    # the f32 maps alone (double outputs NULL)
+    d_c32.zero_()
+    seg.set_frame(5)
+    seg.run_device_maps(d_bgr.data_ptr(), d_cls.data_ptr(), 0, 0, d_c32.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_c32.cpu().numpy(), conf.reshape(-1).astype(np.float32))
+
+
 @pytest.mark.parametrize("compose", ["0", "1"])
 def test_fused_epilogues_equal_the_unfused_ops(model_dir, monkeypatch, compose):
     """keep_blobs keeps max-unpool and the 1x1 classifier as their own kernels; the default build scatters from the

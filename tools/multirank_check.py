@@ -42,7 +42,9 @@ def main():
         stream = torch.cuda.current_stream(dev)
         base = rec.data_ptr()
         seg.set_frame(100 + r)
-        seg.run_device(d_bgr.data_ptr(), base + offs["classes"], base + offs["confidence"], base + offs["entropy"], stream.cuda_stream)
+        d_conf, d_ent = torch.empty(hw, dtype=torch.float64, device=dev), torch.empty(hw, dtype=torch.float64, device=dev)
+        seg.run_device_maps(d_bgr.data_ptr(), base + offs["classes"], d_conf.data_ptr(), d_ent.data_ptr(), base + offs["confidence"],
+                            base + offs["entropy"], stream.cuda_stream)
         orb_l.enqueue_device(d_gl.data_ptr(), NET_H, NET_W, NET_W, base + offs["kp_left"], base + offs["desc_left"], base + 8)
         orb_r.enqueue_device(d_gr.data_ptr(), NET_H, NET_W, NET_W, base + offs["kp_right"], base + offs["desc_right"], base + 16)
         rec[:8].view(torch.int64).fill_(1000 + r)
@@ -50,6 +52,10 @@ def main():
         orb_r.stream_wait(stream.cuda_stream)
         torch.cuda.synchronize(dev)
         assert orb_l.device_status() == 0 and orb_r.device_status() == 0
+        # the record's f32 maps are the rounded double maps
+        u = record.unpack(rec.cpu().numpy(), NET_H, NET_W, kp_cap)
+        assert np.array_equal(u["confidence"].reshape(-1), d_conf.cpu().numpy().astype(np.float32))
+        assert np.array_equal(u["entropy"].reshape(-1), d_ent.cpu().numpy().astype(np.float32))
         return rec, kp_cap
 
     seg = BayesianSegNet(BayesianSegNetParams(proto, model), device=local, seed=1234, T=T)
