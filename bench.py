@@ -281,7 +281,8 @@ def main():
         # waves of 144).  A default NCCL all-gather takes a dozen SMs and would push them into a third wave, so keep it to a
         # few channels: 3.5 MB per rank needs little bandwidth (measured at N=2 with the earlier 6.4 MB record: 8 channels 1278 fps,
         # 2: 1425, 1: 1443).
-        nch = "1" if world <= 2 else "2"  # measured: N=4 2 channels 2899 fps (default 2499); N=8 2 channels 5355, 4: 5175 (default 5013)
+        # measured with the 3.5 MB record (profiles/r2_scaling.md): N=8 2 channels 9972 frames/s, 4 channels 10396 (N=1 1324)
+        nch = "1" if world <= 2 else ("2" if world <= 4 else "4")
         os.environ.setdefault("NCCL_MAX_NCHANNELS", nch)
         os.environ.setdefault("NCCL_MAX_CTAS", nch)
         dist.init_process_group("nccl", device_id=dev)
@@ -427,6 +428,10 @@ def main():
     out_pageable = tuple(np.empty_like(a) for a in out_np)
     pyr_pageable = [[np.empty_like(a) for a in lst] for lst in pyr_np]
 
+    ev_e2e = [torch.cuda.Event() for _ in range(NBUF)]
+    ev_up = [torch.cuda.Event() for _ in range(NBUF)]
+    e2e_used = [False] * NBUF
+
     def host_step(i, order="reference", pinned=True):
         """One frame through the reference-facing calls on HOST buffers; each call is synchronous for its caller (host image in,
         host results out, copies inside).  order "reference": segmentImage returns before the two extractor threads start
@@ -434,6 +439,14 @@ def main():
         j = i % n_frames
         left, gl, gr = (h_fr if pinned else h_fr_pageable)[j]
         outs, pyr = (out_np, pyr_np) if pinned else (out_pageable, pyr_pageable)
+        if world > 1:
+            # N > 1: the frame's record is shared with every rank.  segmentImage leaves the record's maps (classes + f32
+            # confidence / entropy) on the device next to the host results, so only the header and the keypoints go back up.
+            k = i % NBUF
+            if e2e_used[k]:
+                ev_e2e[k].synchronize()  # record k's previous gather (NBUF frames ago) has read d_rec[k] / the upload has read h_rec[k]
+            base = d_rec[k].data_ptr()
+            seg.set_record_outputs(base + o_cls, base + o_conf, base + o_ent)
         if order == "reference":
             res = seg.segmentImage(left, out=outs)
             fl_ = pool.submit(orb_l, gl, None, want_pyramid=True, pyramid_buffers=pyr[0])
@@ -444,12 +457,20 @@ def main():
             res = seg.segmentImage(left, out=outs)
         out = [fl_.result(), fr_.result()]
         if world > 1:
-            # N > 1: the frame's record is shared with every rank -- pack the host results, upload, all-gather, wait
-            k = i % NBUF
-            record.pack_host(h_rec[k], hw, kp_cap, rank * 100000 + i, res[0], res[1], res[2], out[0][0], out[0][1], out[1][0], out[1][1])
-            d_rec[k].copy_(h_rec_t[k], non_blocking=True)
-            dist.all_gather_into_tensor(d_all[k], d_rec[k])
-            torch.cuda.current_stream(dev).synchronize()
+            record.pack_host_part(h_rec[k], hw, kp_cap, rank * 100000 + i, out[0][0], out[0][1], out[1][0], out[1][1])
+            d_rec[k][:record.HEADER].copy_(h_rec_t[k][:record.HEADER], non_blocking=True)
+            d_rec[k][o_kp:].copy_(h_rec_t[k][o_kp:], non_blocking=True)
+            ev_up[k].record(stream)
+            # the all-gather of frame i runs on the side stream under frame i+1's calls; frame i-1's must have landed before this
+            # step returns (one frame of pipelining; the timed region ends with a device synchronize, so the last one is inside it)
+            with torch.cuda.stream(side):
+                side.wait_event(ev_up[k])
+                dist.all_gather_into_tensor(d_all[k], d_rec[k])
+                ev_e2e[k].record(side)
+            e2e_used[k] = True
+            kp = (i - 1) % NBUF
+            if e2e_used[kp] and kp != k:
+                ev_e2e[kp].synchronize()
         return res, out
 
     def barrier():
@@ -509,6 +530,7 @@ def main():
             reps.append(time.perf_counter() - t0)
         e2e_times[name] = float(np.median(reps))
     e2e_elapsed = e2e_times["reference_order_pinned"]
+    seg.set_record_outputs()
     clocks = sampler.stop() if rank == 0 else None
     n_kp = len(out[0][0]) + len(out[1][0])
     # per step, counted from the copies the three calls make: the cropped colour image and the two gray images go up; the three maps,
@@ -521,6 +543,7 @@ def main():
         h2d = hw * 3 + 2 * hw + n_kp * 8
         d2h = hw * 17 + n_kp * 36 + 2 * (32768 * 4 + 9 * 4) + pyr_bytes
     if world > 1:
+        h2d += record.HEADER + 2 * kp_cap * 60  # the record's header and keypoint / descriptor blocks go back up for the gather
         names = sorted(e2e_times)
         tt = torch.tensor([elapsed] + [e2e_times[n] for n in names], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -81,6 +81,10 @@ int sivo_segnet_run(sivo_segnet_t* h, const uint8_t* bgr, int rows, int cols, si
  * (a cudaStream_t; NULL = the handle's own stream).  No host synchronisation. */
 int sivo_segnet_run_device(sivo_segnet_t* h, const uint8_t* bgr_device, uint8_t* classes_device,
                            double* confidence_device, double* entropy_device, void* stream);
+/* Multi-GPU callers share a packed per-frame record: after this call every sivo_segnet_run additionally leaves the
+ * classes (u8) and single-precision copies of the confidence / entropy maps at these DEVICE addresses, complete when it returns,
+ * so the record's maps never travel host -> device.  All NULL switches it off. */
+int sivo_segnet_set_record_outputs(sivo_segnet_t* h, uint8_t* classes_device, float* confidence_f32_device, float* entropy_f32_device);
 /* The same with additional single-precision copies of the two maps (any output may be NULL): what the packed per-frame record
  * of the multi-GPU path carries (classes u8 + entropy f32 + confidence f32), written straight into it by the MC
  * reduction; the double maps stay the operator's outputs (bayesian_segnet.cpp:192-203, 262-276 compute in double). */

@@ -96,6 +96,13 @@ int sivo_segnet_run_device(sivo_segnet_t* h, const uint8_t* bgr_device, uint8_t*
   });
 }
 
+int sivo_segnet_set_record_outputs(sivo_segnet_t* h, uint8_t* classes_device, float* confidence_f32_device, float* entropy_f32_device) {
+  return guarded([&] {
+    if (!h) fail(SIVO_EINVAL, "null handle");
+    h->impl->set_record_outputs(classes_device, confidence_f32_device, entropy_f32_device);
+  });
+}
+
 int sivo_segnet_run_device_maps(sivo_segnet_t* h, const uint8_t* bgr_device, uint8_t* classes_device, double* confidence_device,
                                 double* entropy_device, float* confidence_f32_device, float* entropy_f32_device, void* stream) {
   return guarded([&] {

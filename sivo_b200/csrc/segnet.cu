@@ -665,12 +665,14 @@ void SegNet::run_host(const uint8_t* bgr, int rows, int cols, size_t stride, uin
   static const int n_bands = [] { const char* e = std::getenv("SIVO_B200_READBACK_BANDS"); return e ? std::max(1, std::min(16, atoi(e))) : 1; }();  // opt-in: measured no gain with the extractors' copies sharing the D2H engine
   const Op& last = ops_.back();
   const TensorView* lv = last.kind == Op::Reduce ? &tensors_[last.in]->v : nullptr;
-  const bool banded = n_bands > 1 && !profiling_ && lv && lv->cs == 16 && lv->c <= 16 && (classes || conf || ent) && H_ >= n_bands;
+  const bool to_record = rec_classes_ || rec_conf32_ || rec_ent32_;
+  const bool banded = n_bands > 1 && !to_record && !profiling_ && lv && lv->cs == 16 && lv->c <= 16 && (classes || conf || ent) && H_ >= n_bands;
   if (!banded) {
-    run_device(d_bgr_.as<uint8_t>(), d_classes_.as<uint8_t>(), d_conf_.as<double>(), d_ent_.as<double>(), stream_);
+    run_device(d_bgr_.as<uint8_t>(), d_classes_.as<uint8_t>(), d_conf_.as<double>(), d_ent_.as<double>(), stream_, rec_conf32_, rec_ent32_);
     if (classes) SIVO_CUDA(cudaMemcpyAsync(hc, d_classes_.p, hw, cudaMemcpyDeviceToHost, stream_));
     if (conf) SIVO_CUDA(cudaMemcpyAsync(hf, d_conf_.p, hw * sizeof(double), cudaMemcpyDeviceToHost, stream_));
     if (ent) SIVO_CUDA(cudaMemcpyAsync(he, d_ent_.p, hw * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    if (rec_classes_) SIVO_CUDA(cudaMemcpyAsync(rec_classes_, d_classes_.p, hw, cudaMemcpyDeviceToDevice, stream_));
     SIVO_CUDA(cudaStreamSynchronize(stream_));
   } else {
     if (!copy_stream_) SIVO_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));

@@ -66,6 +66,11 @@ class SegNet {
   int classes() const { return n_classes_; }
   void set_frame(uint64_t f) { frame_ = f; }
   void run_host(const uint8_t* bgr, int rows, int cols, size_t stride, uint8_t* classes, double* conf, double* ent);
+  // segmentImage (run_host) additionally leaves the classes and f32 copies of the two maps at these device addresses, complete
+  // when it returns (all NULL: off)
+  void set_record_outputs(uint8_t* classes_dev, float* conf32_dev, float* ent32_dev) {
+    rec_classes_ = classes_dev; rec_conf32_ = conf32_dev; rec_ent32_ = ent32_dev;
+  }
   // conf32 / ent32 (optional): single-precision copies of the two maps, e.g. straight into the packed multi-GPU record
   void run_device(const uint8_t* bgr_dev, uint8_t* classes_dev, double* conf_dev, double* ent_dev, cudaStream_t s, float* conf32_dev = nullptr,
                   float* ent32_dev = nullptr);
@@ -117,6 +122,10 @@ class SegNet {
   bool skip_reduce_ = false;      // set by run_host around run_device: the op list stops before the Reduce op
   cudaStream_t copy_stream_ = nullptr;
   std::vector<cudaEvent_t> band_ev_;
+  // device-resident copies run_host leaves for a packed multi-GPU record (set_record_outputs)
+  uint8_t* rec_classes_ = nullptr;
+  float* rec_conf32_ = nullptr;
+  float* rec_ent32_ = nullptr;
 };
 
 // conv_tc.cu -- tcgen05 implicit-GEMM convolution

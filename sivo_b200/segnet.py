@@ -107,6 +107,10 @@ class BayesianSegNet:
         L.check(L.lib().sivo_segnet_run_device(self._h, C.c_void_p(bgr_ptr), C.c_void_p(classes_ptr), C.c_void_p(conf_ptr),
                                                C.c_void_p(ent_ptr), C.c_void_p(stream)))
 
+    def set_record_outputs(self, classes_ptr: int = 0, conf32_ptr: int = 0, ent32_ptr: int = 0):
+        """segmentImage additionally leaves classes + f32 maps at these device addresses (a packed multi-GPU record); 0s: off."""
+        L.check(L.lib().sivo_segnet_set_record_outputs(self._h, C.c_void_p(classes_ptr), C.c_void_p(conf32_ptr), C.c_void_p(ent32_ptr)))
+
     def run_device_maps(self, bgr_ptr: int, classes_ptr: int, conf_ptr: int, ent_ptr: int, conf32_ptr: int, ent32_ptr: int, stream: int = 0):
         """run_device plus single-precision copies of the two maps (the packed multi-GPU record's layout); any pointer may be 0."""
         L.check(L.lib().sivo_segnet_run_device_maps(self._h, C.c_void_p(bgr_ptr), C.c_void_p(classes_ptr), C.c_void_p(conf_ptr),

@@ -223,6 +223,16 @@ def test_run_device_maps_writes_rounded_single_precision_copies(model_dir):
     assert np.array_equal(d_c64.cpu().numpy().reshape(h, w_), conf) and np.array_equal(d_e64.cpu().numpy().reshape(h, w_), ent)
     assert np.array_equal(d_c32.cpu().numpy(), conf.reshape(-1).astype(np.float32))
     assert np.array_equal(d_e32.cpu().numpy(), ent.reshape(-1).astype(np.float32))
+    # segmentImage with record outputs set leaves the same three device-resident copies
+    d_cls.zero_(), d_c32.zero_(), d_e32.zero_()
+    seg.set_record_outputs(d_cls.data_ptr(), d_c32.data_ptr(), d_e32.data_ptr())
+    seg.set_frame(5)
+    cls_b, conf_b, ent_b = (np.array(a) for a in seg.segmentImage(left))
+    seg.set_record_outputs()
+    assert np.array_equal(cls_b, cls) and np.array_equal(conf_b, conf) and np.array_equal(ent_b, ent)
+    assert np.array_equal(d_cls.cpu().numpy().reshape(h, w_), cls)
+    assert np.array_equal(d_c32.cpu().numpy(), conf.reshape(-1).astype(np.float32))
+    assert np.array_equal(d_e32.cpu().numpy(), ent.reshape(-1).astype(np.float32))
     # the f32 maps alone (double outputs NULL)
     d_c32.zero_()
     seg.set_frame(5)

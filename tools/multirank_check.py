@@ -58,6 +58,27 @@ def main():
         assert np.array_equal(u["entropy"].reshape(-1), d_ent.cpu().numpy().astype(np.float32))
         return rec, kp_cap
 
+    def run_frame_host(r, seg, orb_l, orb_r):
+        """The same record built the way bench.py's N > 1 e2e step does: the operator calls on host buffers, segmentImage leaving
+        the record's maps on the device, header + keypoints packed on the host and uploaded."""
+        left, gl, gr = frames(1, start=r)[0]
+        kp_cap = orb_l.capacity()
+        offs = record.offsets(hw, kp_cap)
+        rec = torch.zeros(record.record_bytes(hw, kp_cap), dtype=torch.uint8, device=dev)
+        base = rec.data_ptr()
+        seg.set_record_outputs(base + offs["classes"], base + offs["confidence"], base + offs["entropy"])
+        seg.set_frame(100 + r)
+        seg.segmentImage(left)
+        seg.set_record_outputs()
+        (kl, dl), (kr, dr) = orb_l(gl, None)[:2], orb_r(gr, None)[:2]
+        h = np.zeros(rec.numel(), np.uint8)
+        record.pack_host_part(h, hw, kp_cap, 1000 + r, kl, dl, kr, dr)
+        ht = torch.from_numpy(h)
+        rec[:record.HEADER].copy_(ht[:record.HEADER])
+        rec[offs["kp_left"]:].copy_(ht[offs["kp_left"]:])
+        torch.cuda.synchronize(dev)
+        return rec
+
     seg = BayesianSegNet(BayesianSegNetParams(proto, model), device=local, seed=1234, T=T)
     orb_l, orb_r = ORBextractor(nfeat, 1.2, 8, 20, 7, device=local), ORBextractor(nfeat, 1.2, 8, 20, 7, device=local)
     rec, kp_cap = run_frame(rank, seg, orb_l, orb_r)
@@ -73,6 +94,10 @@ def main():
             same = a["frame_id"] == 1000 + r and all(np.array_equal(a[k], b[k]) for k in ("classes", "confidence", "entropy", "desc_left", "desc_right")) \
                 and a["kp_left"].tobytes() == b["kp_left"].tobytes() and a["kp_right"].tobytes() == b["kp_right"].tobytes() \
                 and len(a["kp_left"]) > 300 and len(a["kp_right"]) > 300
+            # ... and the record the host-call (e2e) path builds for the same frame is the same bytes where both define them
+            c = record.unpack(run_frame_host(r, seg, orb_l, orb_r).cpu().numpy(), NET_H, NET_W, kp_cap)
+            same = same and all(np.array_equal(a[k], c[k]) for k in ("classes", "confidence", "entropy", "desc_left", "desc_right")) \
+                and a["kp_left"].tobytes() == c["kp_left"].tobytes() and a["kp_right"].tobytes() == c["kp_right"].tobytes() and c["frame_id"] == 1000 + r
             print(f"rank {r}: frame_id {a['frame_id']}, {len(a['kp_left'])}+{len(a['kp_right'])} keypoints, record {'OK' if same else 'MISMATCH'}")
             ok = ok and same
         # the records of different ranks really are different frames
