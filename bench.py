@@ -244,7 +244,10 @@ def workload_config(args, T):
             "calls": "value: run_device (graph replay) + the two extractors on two host threads, inputs resident in HBM.  "
                      "e2e: the reference's call order -- segmentImage(host image) returns, THEN the two ORBextractor calls on two "
                      "threads (src/orbslam/Frame.cc:125-129), page-locked caller buffers; e2e_variants holds the same with the three "
-                     "calls issued concurrently (one-line Frame.cc change, INTEGRATION.md) and with pageable caller buffers"}
+                     "calls issued concurrently (one-line Frame.cc change, INTEGRATION.md) and with pageable caller buffers.  "
+                     "N > 1: every step also shares the frame's packed record (classes u8 + f32 maps + keypoints, 3.5 MB) with all "
+                     "ranks by one NCCL all-gather -- in `value` written on the device and gathered under the next frame, in `e2e` "
+                     "the maps stay on the device (set_record_outputs), header + keypoints go back up, the gather is pipelined one frame"}
 
 
 def main():
