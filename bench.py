@@ -191,7 +191,7 @@ def run_reference(args, rank, world):
         return
     import gen_prototxt
     from sivo_b200.prototxt import load_net
-    T = args.T or (6 if args.model == "basic" else 12)
+    T = args.T or (6 if args.model == "basic" else (12 if world == 1 else 6))  # the GPU arm's rule: configs[1] / [2] / [3]
     net, proto, model, weights = model_files(args.model, T, os.path.join("/tmp", "sivo_b200_models"))
     weights = weights or load_weights(net, model)
     cores = os.cpu_count() or 1
