@@ -8,6 +8,7 @@
 // *.bin = int32 rows, int32 cols, int32 channels, then the pixels.  `run` dumps classes / confidence / entropy, the blended
 // segmentation image, keypoints, descriptors and the pyramid levels for tests/test_shim.py to compare with the Python mirror
 // of the same C-ABI (bit-identical) and with cv2 (LUT + addWeighted).
+#include <cmath>
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -98,6 +99,15 @@ int main(int argc, char **argv) {
         EXPECT(!kps.empty() && desc.rows == static_cast<int>(kps.size()) && desc.cols == 32);
         EXPECT(ex.GetLevels() == 8 && ex.mvImagePyramid.size() == 8);
         EXPECT(ex.mvImagePyramid[0].rows == gray.rows && ex.mvImagePyramid[0].cols == gray.cols);
+        // the per-level tables Frame / ORBmatcher read through the getters (ORBextractor.cc:420-438)
+        std::vector<float> sf = ex.GetScaleFactors(), isf = ex.GetInverseScaleFactors(), s2 = ex.GetScaleSigmaSquares(),
+                           is2 = ex.GetInverseScaleSigmaSquares();
+        EXPECT(sf.size() == 8 && isf.size() == 8 && s2.size() == 8 && is2.size() == 8);
+        EXPECT(std::fabs(ex.GetScaleFactor() - 1.2) < 1e-6 && sf[0] == 1.0f && s2[0] == 1.0f);
+        for (size_t l = 1; l < sf.size() && l < 8; ++l) {
+            EXPECT(std::fabs(sf[l] - sf[l - 1] * 1.2f) <= 2e-6f * sf[l] && std::fabs(s2[l] - sf[l] * sf[l]) <= 2e-6f * s2[l]);
+            EXPECT(std::fabs(isf[l] * sf[l] - 1.f) < 2e-6f && std::fabs(is2[l] * s2[l] - 1.f) < 2e-6f);
+        }
         dump(out + "/keypoints.bin", kps.data(), kps.size() * sizeof(cv::KeyPoint));
         cv::Mat d = desc.clone();
         dump(out + "/descriptors.bin", d.data, d.total());
